@@ -1,0 +1,613 @@
+/* capi.cu -- host side of the C ABI (include/flint_b200.h).
+ *
+ * Mirrors the object semantics of the reference: flint_erk_t holds what
+ * ERK_class holds (options parsed by Init, counters/status of the last scalar
+ * Integrate, dense-output storage), validation and error codes follow
+ * src/ERKInit.f90:68-190,296-309 and src/ERKIntegrate.f90:94-199.  All compute
+ * is the CUDA kernels; there is no host fallback.
+ */
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/flint_b200.h"
+#include "kargs.h"
+
+using flint::KArgs;
+
+static thread_local std::string g_last_error;
+static long g_launches = 0;
+static double g_last_kernel_ms = 0.0;
+
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+static bool cuda_ok(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+struct flint_sys {
+    int system_id, eventset_id, n, m;
+    double sp[8];
+};
+
+struct DenseStore {                    /* device-resident Xint / Bip of the last Integrate with InterpOn */
+    int device = -1;
+    long N = 0, cap = 0;
+    int nI = 0, pstar = 0;
+    double* dxint = nullptr; double* dbip = nullptr; int* dcount = nullptr;
+    void release()
+    {
+        if (dxint) cudaFree(dxint);
+        if (dbip) cudaFree(dbip);
+        if (dcount) cudaFree(dcount);
+        dxint = dbip = nullptr; dcount = nullptr; N = cap = 0;
+    }
+};
+
+struct flint_erk {
+    /* FLINT_class / ERK_class state (src/FLINT_base.f90:125-211, src/ERK.f90:72-117) */
+    int status = FLINT_SUCCESS;
+    bool inited = false;
+    const flint_sys* sys = nullptr;
+    flint_sys sys_copy{};
+    int method = ERK_DOP853;
+    int max_steps = 0;
+    bool scalar_tol = true;
+    double atol[FLINT_MAX_N]{}, rtol[FLINT_MAX_N]{};
+    bool interp_on = false;
+    int nI = 0; int istates[FLINT_MAX_N]{};
+    double min_step = 0, max_step = 0;
+    double szp[6]{};
+    bool events_on = false;
+    double ev_stepsz[FLINT_MAX_M]{}; int ev_opt[FLINT_MAX_M]{}; double etol[FLINT_MAX_M]{};
+    int arith = FLINT_ARITH_STRICT;
+    int s = 0, sint = 0, p = 8, q = 7, pstar = 7;
+    /* last scalar Integrate (Info) */
+    int total = 0, accepted = 0, rejected = 0, fcalls = 0;
+    double X0 = 0, Xf = 0, hf = 0;
+    double Y0[FLINT_MAX_N]{}, Yf[FLINT_MAX_N]{};
+    /* dense storage */
+    DenseStore dense;
+    bool dense_is_scalar = false;
+    bool dense_allocated = false;      /* allocated(me%Xint) */
+};
+
+/* ------------------------------------------------------------------ misc */
+static const char* const kErrorStrings[17] = {   /* src/FLINT_base.f90:64-82 */
+    "Successfully Completed", "Termination Event Occurred", "Problem appears to be stiff", "Unknown error",
+    "Incorrect user-provided parameters", "Maximum integration steps reached", "Memory allocation error",
+    "Memory deallocation error", "Incorrect dimensions", "Step size reduced to very small value",
+    "Incorrect interpolation states", "Incorrect interpolation array provided", "Interpolation is not enabled",
+    "Init is required", "Incorrect event-related parameters ", "Event root finding failed",
+    "Incorrect step size for the non-adaptive option" };
+
+extern "C" const char* flint_status_string(int s) { return (s >= 0 && s <= 16) ? kErrorStrings[s] : kErrorStrings[3]; }
+extern "C" const char* flint_last_error(void) { return g_last_error.c_str(); }
+extern "C" long flint_b200_launch_count(void) { return g_launches; }
+extern "C" double flint_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+extern "C" int flint_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+/* ------------------------------------------------------------------ DiffEqSys */
+extern "C" flint_sys_t* flint_sys_create(int system_id, int eventset_id, int n, int m, const double* sysparams, int nsysparams)
+{
+    int need_n = 0, max_m = 0;
+    switch (system_id) {
+    case FLINT_SYS_CR3BP_PLANAR: need_n = 6; max_m = 3; break;
+    case FLINT_SYS_CR3BP_SPATIAL: need_n = 6; max_m = 0; break;
+    case FLINT_SYS_LORENZ: need_n = 3; max_m = 0; break;
+    case FLINT_SYS_TWOBODY: need_n = 6; max_m = 1; break;
+    default: g_last_error = "unknown system_id"; return nullptr;
+    }
+    int ev_m = 0;
+    switch (eventset_id) {
+    case FLINT_EVSET_NONE: ev_m = 0; break;
+    case FLINT_EVSET_CR3BP_SAMPLE3: case FLINT_EVSET_CR3BP_SAMPLE3_TERM: case FLINT_EVSET_CR3BP_SAMPLE3_RESTART:
+        ev_m = (system_id == FLINT_SYS_CR3BP_PLANAR) ? 3 : -1; break;
+    case FLINT_EVSET_XY_CROSSING: ev_m = (system_id == FLINT_SYS_CR3BP_PLANAR) ? 2 : -1; break;
+    case FLINT_EVSET_APSIS: ev_m = (system_id == FLINT_SYS_TWOBODY) ? 1 : -1; break;
+    default: ev_m = -1;
+    }
+    if (n != need_n || ev_m < 0 || m != ev_m || m > max_m || nsysparams < 0 || nsysparams > 8) {
+        g_last_error = "flint_sys_create: n/m/eventset do not match the selected functor";
+        return nullptr;
+    }
+    flint_sys* s = new flint_sys();
+    s->system_id = system_id; s->eventset_id = eventset_id; s->n = n; s->m = m;
+    for (int i = 0; i < 8; ++i) s->sp[i] = (sysparams && i < nsysparams) ? sysparams[i] : 0.0;
+    return s;
+}
+extern "C" void flint_sys_destroy(flint_sys_t* s) { delete s; }
+
+/* ------------------------------------------------------------------ ERK_class */
+extern "C" flint_erk_t* flint_erk_create(void) { return new flint_erk(); }
+extern "C" void flint_erk_destroy(flint_erk_t* e)
+{
+    if (!e) return;
+    e->dense.release();
+    delete e;
+}
+
+static void method_consts(int method, int& s, int& sint, int& p, int& q, int& pstar)
+{
+    switch (method) {   /* src/ButcherTableaus.f90:81-91,207-217,519-529,972-982 */
+    case ERK_DOP54: s = 7; sint = 7; p = 5; q = 4; pstar = 4; break;
+    case ERK_VERNER98R: s = 21; sint = 16; p = 9; q = 8; pstar = 8; break;
+    case ERK_VERNER65E: s = 10; sint = 9; p = 6; q = 5; pstar = 5; break;
+    default: s = 16; sint = 13; p = 8; q = 7; pstar = 7; break;
+    }
+}
+
+extern "C" int flint_erk_init(flint_erk_t* me, const flint_sys_t* DE, int max_steps, const flint_init_opts* o)
+{
+    if (!me || !DE || !o) return fail(FLINT_ERROR_PARAMS, "flint_erk_init: null argument");
+    me->status = FLINT_SUCCESS;                                          /* src/ERKInit.f90:57 */
+    if (o->present & FLINT_INIT_METHOD) me->method = o->method;          /* :60 */
+    if (me->method < ERK_DOP853 || me->method > ERK_VERNER65E) return me->status = FLINT_ERROR_PARAMS;
+    me->sys_copy = *DE; me->sys = &me->sys_copy;                         /* :63 */
+    const int n = DE->n, m = DE->m;
+    if (max_steps <= 0) return me->status = FLINT_ERROR_PARAMS;          /* :68-73 */
+    me->max_steps = max_steps;
+    if (!o->atol || !o->rtol) return me->status = FLINT_ERROR_PARAMS;    /* quirk Q12: mandatory */
+    if (o->n_atol == 1 && o->n_rtol == 1) {                              /* :76-87 */
+        me->scalar_tol = true; me->atol[0] = o->atol[0]; me->rtol[0] = o->rtol[0];
+    } else if (o->n_atol == n && o->n_rtol == n) {
+        me->scalar_tol = false;
+        for (int i = 0; i < n; ++i) { me->atol[i] = o->atol[i]; me->rtol[i] = o->rtol[i]; }
+    } else return me->status = FLINT_ERROR_PARAMS;
+    me->min_step = (o->present & FLINT_INIT_MIN_STEP) ? std::fabs(o->min_step_size) : 2.220446049250313e-16;   /* :92-96 */
+    me->max_step = (o->present & FLINT_INIT_MAX_STEP) ? std::fabs(o->max_step_size) : 0.0;                     /* :100-104 */
+    if (o->present & FLINT_INIT_STEPSZ_PARAMS) {                         /* :108-120 */
+        for (int i = 0; i < 6; ++i) me->szp[i] = o->stepsz_params[i];
+    } else {
+        double beta = 0.0, bm = 0.0;
+        if (me->method == ERK_DOP54) { beta = 0.04; bm = 0.75; }         /* src/ButcherTableaus.f90:95-96 */
+        else if (me->method == ERK_DOP853) { beta = 0.0; bm = 0.2; }     /* :221-222 */
+        me->szp[0] = 0.9; me->szp[1] = 0.333; me->szp[2] = 6.0;          /* src/StepSz.f90:35-44 */
+        me->szp[3] = beta; me->szp[4] = bm; me->szp[5] = 1.0e-4;
+    }
+    me->dense.release(); me->dense_allocated = false;                    /* :123 */
+    if (o->present & FLINT_INIT_INTERP_ON) me->interp_on = o->interp_on != 0;   /* :124-130 */
+    me->events_on = false;                                               /* :135-136 */
+    if (o->present & FLINT_INIT_EVENTS_ON) me->events_on = o->events_on != 0;
+    if (me->events_on) {
+        if (DE->eventset_id == FLINT_EVSET_NONE || m <= 0) me->status = FLINT_ERROR_EVENTPARAMS;   /* :141 */
+        me->nI = n; for (int i = 0; i < n; ++i) me->istates[i] = i + 1;                            /* :144 */
+        if (o->present & FLINT_INIT_EVENT_STEPSZ) {                      /* :147-158 */
+            if (o->n_event_stepsz != m) return me->status = FLINT_ERROR_DIMENSION;
+            for (int i = 0; i < m; ++i) me->ev_stepsz[i] = std::fabs(o->event_stepsz[i]);
+        } else for (int i = 0; i < FLINT_MAX_M; ++i) me->ev_stepsz[i] = 0.0;
+        if (o->present & FLINT_INIT_EVENT_OPTIONS) {                     /* :161-176 */
+            if (o->n_event_options != m) return me->status = FLINT_ERROR_DIMENSION;
+            for (int i = 0; i < m; ++i)
+                if (o->event_options[i] < FLINT_EVENTOPTION_ROOTFINDING || o->event_options[i] > FLINT_EVENTOPTION_STEPEND)
+                    return me->status = FLINT_ERROR_EVENTPARAMS;
+            for (int i = 0; i < m; ++i) me->ev_opt[i] = o->event_options[i];
+        } else for (int i = 0; i < FLINT_MAX_M; ++i) me->ev_opt[i] = FLINT_EVENTOPTION_ROOTFINDING;
+        if (o->present & FLINT_INIT_EVENT_TOL) {                         /* :179-188 */
+            if (o->n_event_tol != m) return me->status = FLINT_ERROR_DIMENSION;
+            for (int i = 0; i < m; ++i) me->etol[i] = std::fabs(o->event_tol[i]);
+        } else for (int i = 0; i < FLINT_MAX_M; ++i) me->etol[i] = 1.0e-6;   /* DEFAULT_EVENTTOL src/ERK.f90:50 */
+    }
+    method_consts(me->method, me->s, me->sint, me->p, me->q, me->pstar);    /* :198-274 */
+    if (o->present & FLINT_INIT_ARITH) {
+        if (o->arith != FLINT_ARITH_STRICT && o->arith != FLINT_ARITH_FMA) return me->status = FLINT_ERROR_PARAMS;
+        me->arith = o->arith;
+    }
+    if (me->interp_on) {                                                 /* :291-335 */
+        if ((o->present & FLINT_INIT_INTERP_STATES) && !me->events_on) {
+            bool bad = o->n_interp_states < 1 || o->n_interp_states > n || !o->interp_states;
+            for (int i = 0; !bad && i < o->n_interp_states; ++i)
+                if (o->interp_states[i] < 1 || o->interp_states[i] > n) bad = true;
+            if (bad) me->status = FLINT_ERROR_INTPSTATES;
+            else { me->nI = o->n_interp_states; for (int i = 0; i < me->nI; ++i) me->istates[i] = o->interp_states[i]; me->status = FLINT_SUCCESS; }
+        } else {
+            me->nI = n; for (int i = 0; i < n; ++i) me->istates[i] = i + 1;
+            me->status = FLINT_SUCCESS;
+        }
+        if (me->status != FLINT_SUCCESS) return me->status;
+        me->dense_allocated = true;     /* IntpMemAllocate: device storage is sized at Integrate time */
+    }
+    me->inited = true;
+    return me->status;
+}
+
+/* ------------------------------------------------------------------ Integrate */
+namespace {
+
+struct DevBuf {                        /* RAII device scratch for FLINT_MEM_HOST staging */
+    std::vector<void*> ptrs;
+    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> T* alloc(size_t count)
+    {
+        void* p = nullptr;
+        if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ptrs.push_back(p);
+        return (T*)p;
+    }
+};
+
+struct ExecCtx {
+    int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0;
+};
+
+}  // namespace
+
+static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double* x0, const double* y0, double* xf,
+                          double* yf, double* stepsz, const flint_int_opts* io, int* counters, int* status,
+                          flint_steps_out* steps, flint_events_out* events, int* stifftest, const ExecCtx& ex,
+                          bool scalar_call)
+{
+    if (!me->inited || !me->sys) return me->status = FLINT_ERROR_INIT_REQD;
+    const flint_sys& sys = *me->sys;
+    const int n = sys.n, m = sys.m;
+    static const flint_int_opts kNoOpts{};
+    if (!io) io = &kNoOpts;
+    int st = FLINT_SUCCESS;
+    const bool const_step = (io->present & FLINT_INT_CONST_STEPSZ) && io->use_const_stepsz;   /* :99-103 (sign check per trajectory, in-kernel) */
+    const bool step_once = (io->present & FLINT_INT_STEP_ADVANCE) && io->step_advance;        /* :113-114 */
+    bool int_steps = false;
+    if (io->present & FLINT_INT_INTSTEPS_ON) {                                                /* :120-127 */
+        if (io->int_steps_on && me->interp_on) st = FLINT_ERROR_PARAMS;
+        else if (io->int_steps_on) int_steps = true;
+    }
+    if (int_steps && !(steps && steps->xint && steps->yint && steps->cap > 0)) st = FLINT_ERROR_PARAMS;   /* :129-140 */
+    const bool stiff_present = stifftest != nullptr;                                          /* :143-154 (range check per trajectory) */
+    if (me->interp_on && !me->dense_allocated) return me->status = FLINT_ERROR_INIT_REQD;    /* :157-161 */
+    bool events_on = me->events_on;
+    unsigned evmask = 0;
+    if (events_on) {                                                                          /* :175-193 */
+        for (int i = 0; i < m; ++i) {
+            const bool on = (io->present & FLINT_INT_EVENT_MASK) ? (io->event_mask[i] != 0) : true;
+            if (on) evmask |= (1u << i);
+        }
+        if (evmask == 0) events_on = false;
+        else if (!events || !events->rec || !events->count) return me->status = FLINT_ERROR_EVENTPARAMS;
+    }
+    if (st != FLINT_SUCCESS) return me->status = st;                                          /* :196-199 */
+    if (N <= 0) return me->status = FLINT_SUCCESS;
+
+    if (!cuda_ok(cudaSetDevice(ex.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
+    const bool dense = me->interp_on;
+    const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, events_on, dense);
+    if (!ke) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "no kernel compiled for method=%d system=%d arith=%d events=%d dense=%d", me->method,
+                 sys.system_id, me->arith, (int)events_on, (int)dense);
+        return me->status = fail(FLINT_ERROR, buf);
+    }
+
+    KArgs a{};
+    a.N = N; a.n = n; a.m = m; a.evset = sys.eventset_id;
+    for (int i = 0; i < 8; ++i) a.sp[i] = sys.sp[i];
+    a.max_steps = me->max_steps;
+    for (int i = 0; i < FLINT_MAX_N; ++i) { a.tol.a[i] = me->atol[i]; a.tol.r[i] = me->rtol[i]; }
+    a.tol.scalar = me->scalar_tol ? 1 : 0;
+    a.hmax_opt = me->max_step;
+    for (int i = 0; i < 6; ++i) a.szp[i] = me->szp[i];
+    a.const_step = const_step; a.step_once = step_once;
+    a.stiff_present = stiff_present; a.stiff_mode = 0;
+    a.events_on = events_on; a.evmask_bits = evmask;
+    for (int i = 0; i < FLINT_MAX_M; ++i) { a.ev_stepsz[i] = me->ev_stepsz[i]; a.ev_opt[i] = me->ev_opt[i]; a.etol[i] = me->etol[i]; }
+    a.x0_scalar = x0_scalar;
+    a.steps_on = int_steps;
+    a.steps_cap = int_steps ? steps->cap : 0;
+    a.ev_cap = events_on ? events->cap : 0;
+    a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
+
+    DevBuf scratch;
+    cudaStream_t s = ex.stream;
+    const size_t szN = (size_t)N;
+    /* ---- device views of the caller's buffers ---- */
+    if (ex.host) {
+        double* d_y0 = scratch.alloc<double>(szN * n);
+        double* d_xf = scratch.alloc<double>(szN);
+        double* d_yf = scratch.alloc<double>(szN * n);
+        int* d_status = scratch.alloc<int>(szN);
+        if (!d_y0 || !d_xf || !d_yf || !d_status) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
+        bool ok = cuda_ok(cudaMemcpyAsync(d_y0, y0, szN * n * 8, cudaMemcpyHostToDevice, s), "H2D y0") &&
+                  cuda_ok(cudaMemcpyAsync(d_xf, xf, szN * 8, cudaMemcpyHostToDevice, s), "H2D xf");
+        a.y0 = d_y0; a.xf = d_xf; a.yf = d_yf; a.status = d_status;
+        if (x0) { double* d = scratch.alloc<double>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, x0, szN * 8, cudaMemcpyHostToDevice, s), "H2D x0"); a.x0 = d; }
+        if (stepsz) { double* d = scratch.alloc<double>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, stepsz, szN * 8, cudaMemcpyHostToDevice, s), "H2D stepsz"); a.stepsz = d; }
+        if (counters) { a.counters = scratch.alloc<int>(szN * 4); ok = ok && a.counters; }
+        if (stifftest) { int* d = scratch.alloc<int>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, stifftest, szN * 4, cudaMemcpyHostToDevice, s), "H2D stifftest"); a.stifftest = d; }
+        if (events_on) {
+            a.ev_count = scratch.alloc<int>(szN);
+            a.ev_rec = scratch.alloc<double>(szN * (size_t)(n + 2) * (size_t)a.ev_cap);
+            ok = ok && a.ev_count && a.ev_rec;
+            /* slots the run does not fill keep the caller's contents */
+            ok = ok && cuda_ok(cudaMemcpyAsync(a.ev_rec, events->rec, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, cudaMemcpyHostToDevice, s), "H2D ev_rec");
+        }
+        if (int_steps) {
+            a.xint = scratch.alloc<double>(szN * (size_t)a.steps_cap);
+            a.yint = scratch.alloc<double>(szN * (size_t)a.steps_cap * n);
+            a.steps_count = steps->count ? scratch.alloc<int>(szN) : nullptr;
+            ok = ok && a.xint && a.yint;
+        }
+        if (!ok) return me->status = (g_last_error.empty() ? fail(FLINT_ERROR_MEMALLOC, "device allocation failed") : FLINT_ERROR);
+    } else {
+        a.x0 = x0; a.y0 = y0; a.xf = xf; a.yf = yf; a.stepsz = stepsz; a.counters = counters; a.status = status;
+        a.stifftest = stifftest;
+        if (events_on) { a.ev_count = events->count; a.ev_rec = events->rec; }
+        if (int_steps) { a.xint = steps->xint; a.yint = steps->yint; a.steps_count = steps->count; }
+        if (!status) return me->status = fail(FLINT_ERROR_PARAMS, "status[] is required");
+    }
+    /* ---- dense storage owned by the object (src/ERKInit.f90:321-332: sized for MaxSteps) ---- */
+    if (dense) {
+        long cap = ex.dense_cap > 0 ? ex.dense_cap : me->max_steps;
+        if (cap > me->max_steps) cap = me->max_steps;
+        DenseStore& D = me->dense;
+        if (D.device != ex.device || D.N != N || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || !D.dxint) {
+            D.release();
+            const size_t nb = szN * (size_t)cap * (size_t)me->nI * (size_t)(me->pstar + 1);
+            if (cudaMalloc(&D.dxint, szN * (size_t)(cap + 1) * 8) != cudaSuccess || cudaMalloc(&D.dbip, nb * 8) != cudaSuccess ||
+                cudaMalloc(&D.dcount, szN * 4) != cudaSuccess) {
+                cudaGetLastError(); D.release();
+                return me->status = fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; set flint_exec.dense_cap");
+            }
+            D.device = ex.device; D.N = N; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar;
+        }
+        a.dense_cap = cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dense_count = D.dcount;
+        me->dense_is_scalar = scalar_call;
+    }
+    /* ---- work distribution: persistent lanes ---- */
+    int dev_sms = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ex.device);
+    int block = ex.block > 0 ? ex.block : FLINT_DEFAULT_BLOCK;
+    block = (block + 31) / 32 * 32;
+    if (block > FLINT_MAX_BLOCK) block = FLINT_MAX_BLOCK;
+    int bps = 0;
+    if (!cuda_ok(ke->occupancy(&bps, block), "occupancy query")) return me->status = FLINT_ERROR;
+    if (bps < 1) bps = 1;
+    if (ex.blocks_per_sm > 0 && ex.blocks_per_sm < bps) bps = ex.blocks_per_sm;
+    long grid = (long)dev_sms * bps;                         /* one resident wave: SM count x resident CTAs */
+    const long need = (N + block - 1) / block;
+    if (grid > need) grid = need;
+    unsigned long long* d_counter = scratch.alloc<unsigned long long>(1);
+    if (!d_counter) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
+    const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
+    if (!cuda_ok(cudaMemcpyAsync(d_counter, &first_free, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) return me->status = FLINT_ERROR;
+    a.work_counter = d_counter;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool timed = !ex.async;
+    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+    cudaError_t le = ke->launch(a, (int)grid, block, s);
+    g_launches += 1;
+    if (timed) cudaEventRecord(e1, s);
+    if (!cuda_ok(le, "kernel launch")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
+
+    if (ex.host) {
+        bool ok = cuda_ok(cudaMemcpyAsync(xf, a.xf, szN * 8, cudaMemcpyDeviceToHost, s), "D2H xf") &&
+                  cuda_ok(cudaMemcpyAsync(yf, a.yf, szN * n * 8, cudaMemcpyDeviceToHost, s), "D2H yf");
+        if (status) ok = ok && cuda_ok(cudaMemcpyAsync(status, a.status, szN * 4, cudaMemcpyDeviceToHost, s), "D2H status");
+        if (stepsz && !const_step) ok = ok && cuda_ok(cudaMemcpyAsync(stepsz, a.stepsz, szN * 8, cudaMemcpyDeviceToHost, s), "D2H stepsz");
+        if (counters) ok = ok && cuda_ok(cudaMemcpyAsync(counters, a.counters, szN * 16, cudaMemcpyDeviceToHost, s), "D2H counters");
+        if (stifftest) ok = ok && cuda_ok(cudaMemcpyAsync(stifftest, a.stifftest, szN * 4, cudaMemcpyDeviceToHost, s), "D2H stifftest");
+        if (events_on) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(events->count, a.ev_count, szN * 4, cudaMemcpyDeviceToHost, s), "D2H ev_count") &&
+                 cuda_ok(cudaMemcpyAsync(events->rec, a.ev_rec, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, cudaMemcpyDeviceToHost, s), "D2H ev_rec");
+        }
+        if (int_steps) {
+            ok = ok && cuda_ok(cudaMemcpyAsync(steps->xint, a.xint, szN * (size_t)a.steps_cap * 8, cudaMemcpyDeviceToHost, s), "D2H xint") &&
+                 cuda_ok(cudaMemcpyAsync(steps->yint, a.yint, szN * (size_t)a.steps_cap * n * 8, cudaMemcpyDeviceToHost, s), "D2H yint");
+            if (steps->count) ok = ok && cuda_ok(cudaMemcpyAsync(steps->count, a.steps_count, szN * 4, cudaMemcpyDeviceToHost, s), "D2H steps_count");
+        }
+        if (!ok) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
+    }
+    if (!ex.async || ex.host) {
+        if (!cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
+    }
+    if (timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        g_last_kernel_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return me->status = FLINT_SUCCESS;
+}
+
+static ExecCtx make_exec(const flint_exec* x)
+{
+    ExecCtx e;
+    if (x) {
+        e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
+        e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
+    }
+    return e;
+}
+
+extern "C" int flint_erk_integrate_batch(flint_erk_t* me, long N, double x0_scalar, const double* x0, const double* y0,
+                                         double* xf, double* yf, double* stepsz, const flint_int_opts* io, int* counters,
+                                         int* status, flint_steps_out* steps, flint_events_out* events, int* stifftest,
+                                         const flint_exec* exec)
+{
+    if (!me) return FLINT_ERROR_PARAMS;
+    if (!y0 || !xf || !yf) return me->status = fail(FLINT_ERROR_PARAMS, "y0, xf and yf are required");
+    return integrate_impl(me, N, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest, make_exec(exec), false);
+}
+
+extern "C" int flint_erk_integrate(flint_erk_t* me, double x0, const double* y0, double* xf, double* yf, double* stepsz,
+                                   const flint_int_opts* io, flint_steps_out* steps, flint_events_out* events, int* stifftest)
+{
+    if (!me) return FLINT_ERROR_PARAMS;
+    if (!y0 || !xf || !yf || !stepsz) return me->status = fail(FLINT_ERROR_PARAMS, "y0, xf, yf and stepsz are required");
+    if (!me->sys) return me->status = FLINT_ERROR_INIT_REQD;
+    const int n = me->sys->n;
+    int counters[4] = {0, 0, 0, 0};
+    int st1 = FLINT_SUCCESS;
+    /* N = 1: SoA [c][j][1] is the transpose of the Fortran-shaped [j][c] outputs */
+    std::vector<double> yint_t, ev_t;
+    flint_steps_out s2{}; flint_events_out e2{};
+    int scount = 0, ecount = 0;
+    if (steps) { yint_t.resize((size_t)steps->cap * n); s2.cap = steps->cap; s2.xint = steps->xint; s2.yint = yint_t.data(); s2.count = &scount; }
+    if (events) { ev_t.resize((size_t)events->cap * (n + 2)); e2.cap = events->cap; e2.rec = ev_t.data(); e2.count = &ecount; }
+    ExecCtx ex;   /* device 0, host memory, synchronous */
+    const double x0s = x0, xf_in = *xf;
+    (void)xf_in;
+    int rc = integrate_impl(me, 1, x0, nullptr, y0, xf, yf, stepsz, io, counters, &st1, steps ? &s2 : nullptr,
+                            events ? &e2 : nullptr, stifftest, ex, true);
+    if (rc != FLINT_SUCCESS) return rc;   /* argument error or CUDA failure: me%status already set */
+    if (st1 == FLINT_ERROR_CONSTSTEPSZ || (st1 == FLINT_ERROR_PARAMS && counters[0] == 0)) return me->status = st1;
+    if (steps) {
+        const long cnt = scount < steps->cap ? scount : steps->cap;
+        for (long j = 0; j < cnt; ++j) for (int c = 0; c < n; ++c) steps->yint[j * n + c] = yint_t[(size_t)c * steps->cap + j];
+        if (steps->count) *steps->count = scount;
+    }
+    if (events) {
+        const long cnt = ecount < events->cap ? ecount : events->cap;
+        for (long j = 0; j < cnt; ++j) for (int c = 0; c < n + 2; ++c) events->rec[j * (n + 2) + c] = ev_t[(size_t)c * events->cap + j];
+        if (events->count) *events->count = ecount;
+    }
+    me->total = counters[0]; me->accepted = counters[1]; me->rejected = counters[2]; me->fcalls = counters[3];
+    me->X0 = x0s; for (int c = 0; c < n; ++c) { me->Y0[c] = y0[c]; me->Yf[c] = yf[c]; }
+    me->Xf = *xf; me->hf = *stepsz;
+    return me->status = st1;
+}
+
+/* ------------------------------------------------------------------ Interpolate */
+static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* yarr, int layout, int* status,
+                            bool has_save, bool save, const ExecCtx& ex, bool scalar_call)
+{
+    if (!me->interp_on) return me->status = FLINT_ERROR_INTP_OFF;                       /* src/ERKInterp.f90:45-48 */
+    const bool dealloc = has_save ? !save : true;                                        /* :52-53 */
+    if (G < 1) return me->status;                                                        /* :56-57 */
+    DenseStore& D = me->dense;
+    if (!D.dxint || D.N <= 0) return me->status = FLINT_ERROR_INTP_OFF;                  /* storage already freed */
+    if (!xarr || !yarr) return me->status = fail(FLINT_ERROR_PARAMS, "xarr and yarr are required");
+    if (!cuda_ok(cudaSetDevice(D.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
+    const long N = D.N;
+    cudaStream_t s = ex.stream;
+    DevBuf scratch;
+    /* monotonicity of the shared grid is a host-side check (:60-68) */
+    std::vector<double> hx;
+    const double* xh = xarr;
+    if (!ex.host) { hx.resize((size_t)G); if (!cuda_ok(cudaMemcpy(hx.data(), xarr, (size_t)G * 8, cudaMemcpyDeviceToHost), "D2H xarr")) return me->status = FLINT_ERROR; xh = hx.data(); }
+    int up = 1, down = 1;
+    for (long i = 0; i + 1 < G; ++i) { if (!(xh[i] < xh[i + 1])) up = 0; if (!(xh[i] > xh[i + 1])) down = 0; }
+    flint::InterpArgs a{};
+    a.N = N; a.G = G; a.nI = D.nI; a.pstar = D.pstar; a.cap = D.cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dcount = D.dcount;
+    a.layout = layout; a.fma = me->arith == FLINT_ARITH_FMA;
+    const size_t ny = (size_t)N * (size_t)G * (size_t)D.nI;
+    double* d_y = nullptr; int* d_st = nullptr;
+    if (ex.host) {
+        double* d_x = scratch.alloc<double>((size_t)G);
+        d_y = scratch.alloc<double>(ny); d_st = scratch.alloc<int>((size_t)N);
+        if (!d_x || !d_y || !d_st) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
+        if (!cuda_ok(cudaMemcpyAsync(d_x, xarr, (size_t)G * 8, cudaMemcpyHostToDevice, s), "H2D xarr")) return me->status = FLINT_ERROR;
+        a.xarr = d_x; a.yarr = d_y; a.status = d_st;
+    } else {
+        a.xarr = xarr; a.yarr = yarr; a.status = status;
+        if (!a.status) { d_st = scratch.alloc<int>((size_t)N); a.status = d_st; }
+    }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.device);
+    if (!cuda_ok(flint::launch_interp(a, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
+    g_launches += 2;
+    std::vector<int> hst;
+    if (ex.host) {
+        hst.resize((size_t)N);
+        if (!cuda_ok(cudaMemcpyAsync(hst.data(), d_st, (size_t)N * 4, cudaMemcpyDeviceToHost, s), "D2H status") ||
+            !cuda_ok(cudaMemcpyAsync(yarr, d_y, ny * 8, cudaMemcpyDeviceToHost, s), "D2H yarr"))
+            return me->status = FLINT_ERROR;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;
+    int rc = me->status;
+    if (ex.host) {
+        if (status) for (long i = 0; i < N; ++i) status[i] = hst[(size_t)i];
+        if (scalar_call && hst[0] != FLINT_SUCCESS) { me->status = hst[0]; return me->status; }   /* :62-76: error return keeps storage */
+    }
+    if (dealloc) { D.release(); me->dense_allocated = false; }                                     /* :114-118 */
+    return rc;
+}
+
+extern "C" int flint_erk_interpolate(flint_erk_t* me, const double* xarr, long G, double* yarr, int has_save, int save_coeffs)
+{
+    if (!me) return FLINT_ERROR_PARAMS;
+    ExecCtx ex;
+    return interpolate_impl(me, xarr, G, yarr, 0, nullptr, has_save != 0, save_coeffs != 0, ex, true);
+}
+
+extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, long G, double* yarr, int layout, int* status,
+                                           int has_save, int save_coeffs, const flint_exec* exec)
+{
+    if (!me) return FLINT_ERROR_PARAMS;
+    if (layout != 0 && layout != 1) return me->status = fail(FLINT_ERROR_PARAMS, "layout must be 0 or 1");
+    return interpolate_impl(me, xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, make_exec(exec), false);
+}
+
+/* ------------------------------------------------------------------ Info (src/ERKInit.f90:346-394) */
+extern "C" int flint_erk_info(const flint_erk_t* me, int* last_status, int* nsteps, int* naccept, int* nreject, int* nfcalls,
+                              int* interp_ready, double* x0, double* y0, double* hf, double* xf, double* yf)
+{
+    if (!me) return FLINT_ERROR_PARAMS;
+    if (last_status) *last_status = me->status;
+    if (nsteps) *nsteps = me->total;
+    if (naccept) *naccept = me->accepted;
+    if (nreject) *nreject = me->rejected;
+    if (nfcalls) *nfcalls = me->fcalls;
+    if (interp_ready) *interp_ready = me->interp_on ? 1 : 0;
+    const int n = me->sys ? me->sys->n : 0;
+    if (x0) *x0 = me->X0;
+    if (y0) for (int c = 0; c < n; ++c) y0[c] = me->Y0[c];
+    if (hf) *hf = me->hf;
+    if (xf) *xf = me->Xf;
+    if (yf) for (int c = 0; c < n; ++c) yf[c] = me->Yf[c];
+    return me->status;
+}
+
+/* ------------------------------------------------------------------ fp64 peak microbenchmark */
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3, x4 = x0 + 4e-3, x5 = x0 + 5e-3,
+           x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+            x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" double flint_b200_measure_fp64_peak(int device, double* sm_clock_mhz_out)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; cudaGetLastError(); return -1.0; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int block = 256, grid = sms * 8, iters = 4096;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)grid * block * 8) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        g_launches += 1;
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * (double)block;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    if (sm_clock_mhz_out) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); *sm_clock_mhz_out = khz / 1000.0; }
+    return best;
+}

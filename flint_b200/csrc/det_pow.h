@@ -28,10 +28,8 @@
 
 #if defined(__CUDACC__)
 #define FLINT_HD __host__ __device__ __forceinline__
-#define FLINT_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define FLINT_HD static inline
-#define FLINT_HD_NOINLINE static
 #endif
 
 FLINT_HD double flint_fma_(double a, double b, double c)
@@ -69,7 +67,7 @@ FLINT_HD double flint_scale2_(double v, int n)
     return v * flint_u2d_((uint64_t)(n + 1023) << 52);
 }
 
-FLINT_HD_NOINLINE double flint_det_pow(double x, double y)
+FLINT_HD double flint_det_pow(double x, double y)
 {
     /* ---- special cases (C99 pow semantics for the non-negative half-line) ---- */
     if (y == 0.0 || x == 1.0) return 1.0;

@@ -1,0 +1,86 @@
+/* kargs.h -- plain structs shared by the host side of the C ABI and the kernels. */
+#ifndef FLINT_B200_KARGS_H
+#define FLINT_B200_KARGS_H
+
+#include <cuda_runtime.h>
+#include "../../include/flint_b200.h"
+
+#ifndef FLINT_BLOCK_THREADS
+#define FLINT_BLOCK_THREADS 128      /* __launch_bounds__ of the integrate kernels */
+#endif
+#ifndef FLINT_MIN_BLOCKS
+#define FLINT_MIN_BLOCKS 4
+#endif
+#define FLINT_DEFAULT_BLOCK FLINT_BLOCK_THREADS
+#define FLINT_MAX_BLOCK FLINT_BLOCK_THREADS
+
+namespace flint {
+
+/* ATol/RTol as Init stores them (scalar or per-component; src/ERKInit.f90:76-87) */
+struct Tol {
+    double a[FLINT_MAX_N], r[FLINT_MAX_N];
+    int scalar;
+    __host__ __device__ __forceinline__ double at(int c) const { return scalar ? a[0] : a[c]; }
+    __host__ __device__ __forceinline__ double rt(int c) const { return scalar ? r[0] : r[c]; }
+};
+
+/* Everything an integrate launch needs; passed by value (constant bank, warp-uniform reads). */
+struct KArgs {
+    long N;
+    int n, m;                    /* DiffEqSys n, m (m <= SYS::M_MAX) */
+    int evset;
+    double sp[8];                /* system parameters */
+    int max_steps;
+    Tol tol;
+    double hmax_opt;             /* MaxStepSize, 0 => |Xf - X0| (src/ERKIntegrate.f90:86,237) */
+    double szp[6];               /* StepSzParams */
+    int const_step, step_once;
+    int stiff_present, stiff_mode;
+    /* events */
+    int events_on;
+    unsigned evmask_bits;        /* static EventMask */
+    double ev_stepsz[FLINT_MAX_M];
+    int ev_opt[FLINT_MAX_M];
+    double etol[FLINT_MAX_M];
+    /* inputs / outputs (device pointers, SoA over trajectories) */
+    double x0_scalar; const double* x0;
+    const double* y0;            /* [n][N] */
+    double* xf;                  /* [N] in/out */
+    double* yf;                  /* [n][N] */
+    double* stepsz;              /* [N] in/out or NULL */
+    int* counters;               /* [4][N] or NULL */
+    int* status;                 /* [N] */
+    int* stifftest;              /* [N] in/out or NULL */
+    long ev_cap; int* ev_count; double* ev_rec;          /* [(n+2)][cap][N] */
+    int steps_on; long steps_cap; double* xint; double* yint; int* steps_count;   /* IntStepsOn output */
+    long dense_cap; double* dxint; double* dbip; int* dense_count; int nI; int istates[FLINT_MAX_N];   /* InterpOn storage */
+    unsigned long long* work_counter;
+};
+
+struct InterpArgs {
+    long N, G;
+    int nI, pstar;
+    long cap;
+    const double* dxint; const double* dbip; const int* dcount;
+    const double* xarr;
+    double* yarr; int layout;        /* 0: [N][G][nI], 1: [nI][G][N] */
+    int* status;                     /* [N] or NULL */
+    int fma;
+};
+cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
+
+/* registry of compiled integrate kernels (filled by static initialisers in inst_*.cu) */
+typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t);
+typedef cudaError_t (*occupancy_fn)(int* blocks_per_sm, int block);
+struct KernelEntry {
+    int method, system;
+    bool fma, events, dense;
+    launch_fn launch;
+    occupancy_fn occupancy;
+};
+void register_kernel(const KernelEntry&);
+const KernelEntry* find_kernel(int method, int system, bool fma, bool events, bool dense);
+int kernel_count();
+
+}  // namespace flint
+#endif

@@ -156,11 +156,16 @@ def emit_array(name, vals, ctype="double"):
     return "FLINT_TABLEAU_CONST %s %s[%d] = {\n    %s\n};\n" % (ctype, name, len(vals), body)
 
 
-def build(ref):
+def load_symbols(ref):
+    """Evaluate every tableau parameter of the reference file; returns {lowercase name: value}."""
     ev = Evaluator()
     for st in load_statements(os.path.join(ref, "src", "ButcherTableaus.f90")):
         ev.feed(st)
-    S = ev.sym
+    return ev.sym
+
+
+def build(ref):
+    S = load_symbols(ref)
     out = []
     report = []
     for M in METHODS:
