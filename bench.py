@@ -1,0 +1,285 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native FLINT ensemble integrator.
+
+Metric (BASELINE.json): CR3BP DOP853 orbits/sec, 2^20-orbit ensemble per GPU, rtol 1e-12,
+atol 1e-15, test_CR3BP event set, weak scaling over GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--arith strict|fma]
+
+A "step" is one pass of the hot path (ERK_class%Integrate for every orbit of the ensemble)
+over one batch of seeded synthetic initial conditions.
+  value  : orbits/s with inputs resident in HBM, timed with CUDA events on the launch stream
+  e2e    : the same through the C-ABI call with pinned HOST buffers (H2D + kernel + D2H timed)
+  roofline: algorithmic fp64 flops (SURVEY.md §8d formula, from the per-trajectory step counters)
+           / kernel time, against the fp64 DFMA peak measured in this run by a register-resident
+           microbenchmark (MEASURED_PEAKS.json carries no fp64 figure)
+  cpu_baseline: the CPU oracle (oracle/, a C++ restatement of the reference; the Fortran reference
+           cannot be compiled here -- no Fortran compiler) on all host cores, on a bounded sample.
+N > 1 is launched by torch.distributed.run (one rank per GPU); there is no collective on the data
+path -- NCCL is used only for the barrier and the max-over-ranks of the timings.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_PER_GPU = 1 << 20
+RTOL = 1e-12
+MAX_EVENTS = 2
+CPU_SAMPLE = 1 << 18          # cpu_baseline leg: ~10 s of CPU work on 16 cores
+REF_STEP_SAMPLE = 1 << 16     # --impl reference: orbits per step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arith", default=os.environ.get("FLINT_BENCH_ARITH", "strict"), choices=["strict", "fma"])
+    ap.add_argument("--orbits", type=int, default=N_PER_GPU, help="orbits per GPU (default: the metric's 2^20)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return None
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def workload_name(n):
+    return ("CR3BP planar Arenstorf ensemble, %d orbits/GPU, y0(1)*(1+1e-6*u), 2.5 periods, DOP853 rtol 1e-12 atol 1e-15, "
+            "events m=3 mask [F,T,F] EventStepSz [1e-5,0,0] ETol [1e-3,1e-9,1e-9] (tests/test_CR3BP.f90 shape; SURVEY.md 8d config 3a)" % n)
+
+
+# --------------------------------------------------------------------------- CPU oracle legs
+def run_oracle_sample(arith, n_sample, start=0, nthreads=0):
+    """Integrate n_sample orbits of the SAME seeded ensemble with the CPU oracle; returns (orbits/s, threads, seconds)."""
+    import cases as K
+    from flint_b200 import problems as P
+    import flint_b200 as F
+    case = K.cr3bp_case(F.ERK_DOP853, RTOL, arith, max_events=MAX_EVENTS)
+    y0 = P.cr3bp_ensemble(n_sample, start=start)
+    t0 = time.perf_counter()
+    o = case.run_oracle(y0, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, int(o["threads"]), dt, o
+
+
+def main_reference(a, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The Fortran sources cannot be
+    compiled in this image (no Fortran compiler), so this is the oracle port on all host threads."""
+    if rank != 0:
+        return
+    arith = 1 if a.arith == "fma" else 0
+    for _ in range(max(a.warmup, 0)):
+        run_oracle_sample(arith, 2048)
+    tot_t, tot_n, threads = 0.0, 0, 1
+    for s in range(a.steps):
+        _, threads, dt, _ = run_oracle_sample(arith, REF_STEP_SAMPLE, start=s * REF_STEP_SAMPLE)
+        tot_t += dt
+        tot_n += REF_STEP_SAMPLE
+    val = tot_n / tot_t
+    line = {"impl": "reference", "metric": "CR3BP DOP853 orbits/sec", "value": val, "unit": "orbits/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a.orbits), "sample": "%d orbits per step of the same seeded ensemble" % REF_STEP_SAMPLE,
+                       "arith": a.arith},
+            "cpu_baseline": {"value": val, "unit": "orbits/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps x %d orbits, OpenMP schedule(dynamic,64), one ERK object per thread" % (a.steps, REF_STEP_SAMPLE)},
+            "e2e": {"value": val, "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main_ours(a, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import flint_b200 as F
+    from flint_b200 import problems as P
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    arith = F.FLINT_ARITH_FMA if a.arith == "fma" else F.FLINT_ARITH_STRICT
+    n = a.orbits
+    sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_DOP853, rtol=RTOL, arith=arith)
+    # rank r owns trajectory indices [r*n, (r+1)*n) of the seeded ensemble: shards, no exchange
+    y0_host = P.cr3bp_ensemble(n, start=rank * n)
+    y0 = torch.from_numpy(y0_host).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    peak_tf, _ = F.measure_fp64_peak(local_rank)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step():
+        r = erk.IntegrateBatch(0.0, y0, xf, StepSz=0.0, MaxEvents=MAX_EVENTS, **ikw)
+        return r
+
+    for _ in range(max(a.warmup, 3)):
+        flush.zero_()
+        r = one_step()
+    # ---------------- timed region: device-resident inputs ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    launches0 = F.launch_count()
+    t_wall0 = time.time()
+    ker_ms = []
+    for _ in range(a.steps):
+        flush.zero_()                      # L2 flush between timed iterations (not inside the event-timed kernel window)
+        r = one_step()                     # synchronous; kernel_ms = CUDA events around the launch on its stream
+        ker_ms.append(r["kernel_ms"])
+    barrier()
+    t_wall1 = time.time()
+    launches = F.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    dev_ms = float(sum(ker_ms))
+    # per-trajectory counters of the last step -> algorithmic flops actually required
+    cnt = r["counters"].cpu().numpy().astype(np.int64)
+    nev = int(r["nEvents"].sum().item())
+    status = r["status"].cpu().numpy()
+    flops_step = P.algorithmic_flops(F.ERK_DOP853, F.FLINT_SYS_CR3BP_PLANAR, 6, int(cnt[0].sum()) + nev, int(cnt[1].sum()) + nev, nev)
+    # ---------------- e2e: host buffers through the C ABI ----------------
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+    h_y0 = pin((6, n), torch.float64)
+    h_y0[:] = y0_host
+    outs = {"Yf": pin((6, n), torch.float64), "status": pin((n,), torch.int32), "counters": pin((4, n), torch.int32),
+            "Xf": pin((n,), torch.float64), "StepSz": pin((n,), torch.float64), "StiffTest": pin((n,), torch.int32),
+            "EventStates": pin((8, MAX_EVENTS, n), torch.float64), "nEvents": pin((n,), torch.int32)}
+    e2e_t = []
+    rh = erk.IntegrateBatch(0.0, h_y0, xf, StepSz=0.0, MaxEvents=MAX_EVENTS, out=outs, device=local_rank, **ikw)   # warm
+    barrier()
+    for _ in range(a.steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        rh = erk.IntegrateBatch(0.0, h_y0, xf, StepSz=0.0, MaxEvents=MAX_EVENTS, out=outs, device=local_rank, **ikw)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    e2e_s = float(sum(e2e_t))
+    h2d = 6 * n * 8 + n * 8 + n * 8 + n * 4                                           # y0, xf, stepsz, stifftest
+    d2h = n * 8 + 6 * n * 8 + n * 4 + n * 8 + 4 * n * 4 + n * 4 + n * 4 + (6 + 2) * MAX_EVENTS * n * 8   # xf,yf,status,stepsz,counters,stiff,evcount,events
+    same = bool(np.array_equal(rh["Yf"], r["Yf"].cpu().numpy()))
+
+    # ---------------- max over ranks ----------------
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    agg = torch.tensor([flops_step, float((status == 0).sum())], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    total_orbits = n * world
+    value = total_orbits * a.steps / (dev_ms_max * 1e-3)
+    e2e_value = total_orbits * a.steps / e2e_s_max
+    achieved_tf = flops_step / (dev_ms / a.steps * 1e-3) / 1e12            # this rank's kernel (the dominant and only kernel of a step)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch_%s" % a.arith)
+        except Exception:
+            traffic = None
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, thr, dt, o = run_oracle_sample(arith, CPU_SAMPLE)
+        # the oracle is also the checker here: the sample is the first CPU_SAMPLE orbits of the timed GPU step
+        k = min(CPU_SAMPLE, n)
+        parity = bool(np.array_equal(o["yf"][:, :k], r["Yf"][:, :k].cpu().numpy()) and
+                      np.array_equal(o["counters"][:, :k], r["counters"][:, :k].cpu().numpy()))
+        cpu = {"value": v, "unit": "orbits/s", "cores": thr, "kind": "port",
+               "sample": "first %d orbits of the same seeded ensemble, %.1f s, OpenMP dynamic; bit-parity with the GPU step: %s" % (CPU_SAMPLE, dt, parity)}
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "CR3BP DOP853 orbits/sec", "value": value, "unit": "orbits/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n), "orbits_total": total_orbits, "parallelism": "shard%d (independent orbits, no collective)" % world,
+                   "arith": a.arith, "l2": "256 MB flush between timed iterations", "timing": "CUDA events on the launch stream, max over ranks",
+                   "success_fraction": float(agg[1]) / total_orbits, "host_and_device_results_identical": same},
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": traffic, "kernel": "erk_integrate_kernel<DOP853,CR3BPPlanar,%s,events>" % a.arith,
+                     "peak_source": "DFMA microbenchmark measured in this run (flint_b200_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                     "algorithmic_flop_per_orbit": flops_step / n},
+        "e2e": {"value": e2e_value, "unit": "orbits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "wall_s_timed_region": t_wall1 - t_wall0,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if a.impl == "reference":
+        main_reference(a, rank, world)
+    else:
+        main_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

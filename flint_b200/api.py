@@ -338,6 +338,16 @@ class ERK:
             h = None if StepSz is None else np.ascontiguousarray(np.broadcast_to(np.asarray(StepSz, dtype=np.float64), (N,))).copy()
             stiff = None if StiffTest is None else np.ascontiguousarray(np.broadcast_to(np.asarray(StiffTest, dtype=np.int32), (N,))).copy()
         out = out or {}
+        if not on_dev:      # caller-provided (e.g. pinned) in/out buffers
+            if out.get("Xf") is not None:
+                out["Xf"][:] = xf
+                xf = out["Xf"]
+            if h is not None and out.get("StepSz") is not None:
+                out["StepSz"][:] = h
+                h = out["StepSz"]
+            if stiff is not None and out.get("StiffTest") is not None:
+                out["StiffTest"][:] = stiff
+                stiff = out["StiffTest"]
         yf = out.get("Yf") if out.get("Yf") is not None else zeros((n, N), f64)
         status = out.get("status") if out.get("status") is not None else zeros((N,), i32)
         counters = (out.get("counters") if out.get("counters") is not None else zeros((4, N), i32)) if want_counters else None
@@ -349,8 +359,8 @@ class ERK:
             steps = _StepsOut(cap, _ptr(xint), _ptr(yint), _ptr(scount))
             res.update(Xint=xint, Yint=yint, nXint=scount)
         if EventStates:
-            rec = full((n + 2, MaxEvents, N), float("nan"), f64)
-            ecount = zeros((N,), i32)
+            rec = out.get("EventStates") if out.get("EventStates") is not None else full((n + 2, MaxEvents, N), float("nan"), f64)
+            ecount = out.get("nEvents") if out.get("nEvents") is not None else zeros((N,), i32)
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
         ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, int(dense_cap), int(block_threads),

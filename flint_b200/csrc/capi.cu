@@ -327,8 +327,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             a.ev_count = scratch.alloc<int>(szN);
             a.ev_rec = scratch.alloc<double>(szN * (size_t)(n + 2) * (size_t)a.ev_cap);
             ok = ok && a.ev_count && a.ev_rec;
-            /* slots the run does not fill keep the caller's contents */
-            ok = ok && cuda_ok(cudaMemcpyAsync(a.ev_rec, events->rec, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, cudaMemcpyHostToDevice, s), "H2D ev_rec");
+            /* slots the run does not fill read back as NaN (all-ones pattern) */
+            ok = ok && cuda_ok(cudaMemsetAsync(a.ev_rec, 0xFF, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, s), "memset ev_rec");
         }
         if (int_steps) {
             a.xint = scratch.alloc<double>(szN * (size_t)a.steps_cap);

@@ -125,7 +125,8 @@ typedef struct { long cap; double* xint; double* yint; int* count; } flint_steps
 
 /* EventStates (src/ERKIntegrate.f90:493,679-681): records [Xev, Yev(1:n), id].
  * scalar : rec[cap][n+2] (Fortran EventStates(n+2,cap)), *count = number of events (may exceed cap)
- * batch  : rec[n+2][cap][N], count[N]                                                            */
+ * batch  : rec[n+2][cap][N], count[N].  FLINT_MEM_HOST: slots not filled read back as NaN;
+ *          FLINT_MEM_DEVICE: slots not filled keep the caller's contents                          */
 typedef struct { long cap; double* rec; int* count; } flint_events_out;
 
 /* Where the batch buffers live and how to run */
