@@ -1,0 +1,124 @@
+"""CPU-side tests of the product: the C-ABI library loads and exports every symbol include/flint_b200.h
+declares, Init validation mirrors the reference's error codes, and compute entry points FAIL LOUDLY
+without a CUDA device (there is no CPU fallback).  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import flint_b200 as F
+from flint_b200 import api, problems as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "flint_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(flint_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 16 and "flint_erk_integrate_batch" in syms
+    for s in syms:
+        assert hasattr(lib, s), "libflint_b200.so does not export %s" % s
+    assert lib.flint_b200_kernel_count() == 96      # 4 methods x (2 systems x 8 + 2 systems x 4) variants
+
+
+def test_enum_values_are_the_references():
+    assert (F.ERK_DOP853, F.ERK_DOP54, F.ERK_VERNER98R, F.ERK_VERNER65E) == (17, 18, 19, 20)       # src/ERK.f90:56-66
+    assert (F.FLINT_EVENTACTION_CHANGESOLY, F.FLINT_EVENTACTION_RESTARTINT, F.FLINT_EVENTACTION_MASK) == (2, 4, 128)
+    hdr = open(os.path.join(ROOT, "include", "flint_b200.h")).read()
+    for name, val in (("FLINT_ERROR_CONSTSTEPSZ", 16), ("FLINT_ERROR_EVENTROOT", 15), ("FLINT_EVENTOPTION_STEPEND", 2)):
+        assert re.search(r"%s = %d\b" % (name, val), hdr)
+
+
+def test_status_strings_verbatim():
+    ref = ["Successfully Completed", "Termination Event Occurred", "Problem appears to be stiff", "Unknown error",
+           "Incorrect user-provided parameters", "Maximum integration steps reached", "Memory allocation error",
+           "Memory deallocation error", "Incorrect dimensions", "Step size reduced to very small value",
+           "Incorrect interpolation states", "Incorrect interpolation array provided", "Interpolation is not enabled",
+           "Init is required", "Incorrect event-related parameters ", "Event root finding failed",
+           "Incorrect step size for the non-adaptive option"]              # src/FLINT_base.f90:64-82
+    assert [F.status_string(i) for i in range(17)] == ref
+
+
+def test_init_validation_matches_reference_codes():
+    s = F.DiffEqSys(F.FLINT_SYS_CR3BP_PLANAR, F.FLINT_EVSET_CR3BP_SAMPLE3, [P.CR3BP_MU])
+    e = F.ERK()
+    ok = dict(ATol=[1e-14], RTol=[1e-11])
+    assert e.Init(s, 1000, Method=F.ERK_DOP853, **ok) == F.FLINT_SUCCESS
+    assert e.Init(s, 0, **ok) == F.FLINT_ERROR_PARAMS                                        # src/ERKInit.f90:68-73
+    assert e.Init(s, 10, ATol=[1e-14, 1e-14], RTol=[1e-11]) == F.FLINT_ERROR_PARAMS          # :76-87
+    assert e.Init(s, 10, ATol=[1e-14] * 6, RTol=[1e-11] * 6) == F.FLINT_SUCCESS
+    assert e.Init(s, 10, EventsOn=True, EventStepSz=[1e-5, 0], **ok) == F.FLINT_ERROR_DIMENSION       # :147-158
+    assert e.Init(s, 10, EventsOn=True, EventOptions=[0, 1, 3], **ok) == F.FLINT_ERROR_EVENTPARAMS    # :161-176
+    assert e.Init(s, 10, EventsOn=True, EventTol=[1e-9], **ok) == F.FLINT_ERROR_DIMENSION             # :179-188
+    assert e.Init(s, 10, InterpOn=True, InterpStates=[1, 7], **ok) == F.FLINT_ERROR_INTPSTATES        # :296-304
+    assert e.Init(s, 10, InterpOn=True, InterpStates=[2, 4], **ok) == F.FLINT_SUCCESS
+    noev = F.DiffEqSys(F.FLINT_SYS_LORENZ, F.FLINT_EVSET_NONE, P.LORENZ_PARAMS)
+    assert F.ERK().Init(noev, 10, EventsOn=True, **ok) == F.FLINT_ERROR_EVENTPARAMS          # :141 (G not associated)
+    # faithful quirk: with InterpOn left on from an earlier Init the InterpStates block resets the status (:304-308)
+    assert e.Init(noev, 10, EventsOn=True, **ok) == F.FLINT_SUCCESS
+    with pytest.raises(ValueError):
+        F.DiffEqSys(F.FLINT_SYS_LORENZ, F.FLINT_EVSET_APSIS, P.LORENZ_PARAMS)               # event set of another system
+
+
+def test_integrate_argument_checks_and_loud_failure_without_gpu():
+    s = F.DiffEqSys(F.FLINT_SYS_TWOBODY, F.FLINT_EVSET_NONE, [P.TBP_GM])
+    e = F.ERK()
+    assert e.Init(s, 100, Method=F.ERK_DOP54, ATol=[1e-12], RTol=[1e-9], InterpOn=True) == 0
+    y0 = P.perturbed_ensemble(P.TBP_Y0, 8)
+    r = e.IntegrateBatch(0.0, y0, 10.0, IntStepsOn=True)                # IntStepsOn with InterpOn: src/ERKIntegrate.f90:120-127
+    assert r["rc"] == F.FLINT_ERROR_PARAMS
+    e2 = F.ERK()
+    assert e2.Interpolate([0.0, 1.0])[0] in (F.FLINT_ERROR_INTP_OFF, F.FLINT_ERROR_INIT_REQD)
+    if api.lib().flint_b200_device_count() == 0:
+        assert e.Init(s, 100, Method=F.ERK_DOP54, ATol=[1e-12], RTol=[1e-9]) == 0
+        with pytest.raises(RuntimeError, match="cuda|CUDA"):
+            e.IntegrateBatch(0.0, y0, 10.0)                             # no device, no fallback: loud
+        r = e.Integrate(0.0, P.TBP_Y0, 10.0)
+        assert r["status"] == F.FLINT_ERROR and "CUDA" in F.last_error().upper() or "cuda" in F.last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """The product (flint_b200/, include/) must not include, import or link anything under oracle/."""
+    bad = []
+    for root in (os.path.join(ROOT, "flint_b200"), os.path.join(ROOT, "include")):
+        for dp, _, fns in os.walk(root):
+            if "_build" in dp:
+                continue
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dp, fn)).read()
+                    if re.search(r"oracle_api|liboracle|oracle/|import oracle|from oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_seeded_ensembles_are_reproducible_and_sliceable():
+    a = P.cr3bp_ensemble(1000)
+    b = P.cr3bp_ensemble(100, start=500)
+    assert np.array_equal(a[:, 500:600], b)
+    u = P.uniform01(np.arange(200000))
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+    assert (a[0] >= 0.994).all() and (a[0] <= 0.994 * (1 + 1e-6)).all() and (a[4] == P.ARENSTORF_Y0[4]).all()
+
+
+def test_generated_sources_are_current():
+    """tools/gen_tableaus.py output matches what is committed (only where the reference tree is present)."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present on this machine")
+    import subprocess, sys, tempfile, shutil
+    tmp = tempfile.mkdtemp()
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_tableaus.py"), "--root", tmp], check=True,
+                       capture_output=True)
+        for rel in ("flint_b200/csrc/flint_tableaus.h", "oracle/oracle_tableaus.h"):
+            assert open(os.path.join(tmp, rel)).read() == open(os.path.join(ROOT, rel)).read(), rel
+    finally:
+        shutil.rmtree(tmp)
