@@ -99,6 +99,7 @@ __device__ __forceinline__ void brent_root(double a, double b, double ya, double
 template <class METHOD, class SYS>
 struct EvCtx {
     static constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
+    /* the accepted step whose events must be located */
     double X, h, h_stage;
     double Y[N], Y1[N], F0old[N], ENY[N];
     double EV0[M], EV1[M];
@@ -107,6 +108,10 @@ struct EvCtx {
     int action, st, fcalls, evcount;
     bool LAST, bip_counted, haveB;
     double B[PS + 1][N];
+    /* what the deferred commit needs besides (and returns through X, h, Y1 = new Y, F0new = new F0) */
+    double F0new[N], Err, hbyhopt, hbyhoptOld, hmax;
+    int acc;
+    bool lastRej;
 };
 
 /* Rematerialise the stage vectors of the current step (recompute it from X, Y, F0) and build the
@@ -262,6 +267,83 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
     for (int i = 0; i < M; ++i) c.EV1[i] = EV1[i][0];                   /* what `EV0 = EV1` (:550) carries to the next step */
 }
 
+/* ---- the tail of an accepted step (:555-635): dense store, stale-action quirk, natural-step output,
+ * advance, new step size, too-small test.  Shared by the hot path (state in registers) and by the
+ * deferred event commit (state in the local-memory context). ---- */
+template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
+__device__ __forceinline__ void commit_tail(const KArgs& p, long idx, bool eventsOn, int evAction, double hSign, double hmax,
+        double& X, double (&Y)[SYS::N], double (&F0)[SYS::N], double& h_io, double& hbyhoptOld, bool& lastRej, bool LAST, int& st,
+        int& fcalls, int acc, double h, double (&Y1)[SYS::N], const double (&F0new)[SYS::N], double Err, double hbyhopt,
+        bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N])
+{
+    constexpr int N = SYS::N, PS = METHOD::PSTAR;
+    const long NN = p.N;
+    const bool const_step = p.const_step != 0;
+    if constexpr (DENSE) {                                              /* :555-566 */
+        if (!bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }
+        if (acc <= p.dense_cap) {
+            p.dxint[(long)acc * NN + idx] = X + h;
+            for (int j = 0; j <= PS; ++j)
+                for (int ii = 0; ii < p.nI; ++ii) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
+                    p.dbip[(((long)j * p.nI + ii) * p.dense_cap + (acc - 1)) * NN + idx] = v;
+                }
+        }
+    }
+    if (EVENTS && eventsOn) {                                           /* :572-582 (quirks Q4, Q5) */
+        const int act = evAction & 0x7f;
+        if (act == FLINT_EVENTACTION_RESTARTINT) fcalls += 1;
+        else if (act == FLINT_EVENTACTION_CHANGESOLY) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) Y1[c] = ENY[c];
+            fcalls += 1;
+        }
+    }
+    if (p.steps_on && acc < p.steps_cap) {                              /* :585-588 */
+        p.xint[(long)acc * NN + idx] = X + h;
+#pragma unroll
+        for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + acc) * NN + idx] = Y1[c];
+    }
+    X = X + h;                                                          /* :591-592 */
+#pragma unroll
+    for (int c = 0; c < N; ++c) { Y[c] = Y1[c]; F0[c] = F0new[c]; }
+    double hnew;
+    if (!const_step) {                                                  /* :595-605, src/StepSz.f90:156-168 */
+        const double SFl = p.szp[0], SFmin = p.szp[1], SFmax = p.szp[2], beta = p.szp[3];
+        if (beta != 0.0) hbyhopt = hbyhopt / flint_det_pow(hbyhoptOld, beta);
+        hnew = h * dmin(SFmax, dmax(SFmin, SFl / hbyhopt));
+        hbyhoptOld = dmax(Err, hbyhoptOld);
+        if (fabs(hnew) > hmax) hnew = hSign * hmax;
+        if (lastRej) hnew = hSign * dmin(fabs(hnew), fabs(h));
+        lastRej = false;
+    } else hnew = h;
+    h_io = hnew;                                                        /* :627 */
+    if (!const_step && !LAST && fabs(hnew) * 0.01 <= fabs(X) * kEps) st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
+}
+
+/* ---- deferred commit of a step with events to locate.  Called at the top of the lane loop, where only
+ * the loop-carried state is live: the step's data was stashed in the context when the sign change was
+ * seen, so nothing of the hot step has to survive the call.  Runs the rare path, then the commit tail. ---- */
+template <class METHOD, class SYS, bool FMA, bool DENSE>
+__device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& p, EvCtx<METHOD, SYS>& c, long idx, double hSign)
+{
+    constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
+    event_rare_path<METHOD, SYS, FMA>(sys, p, c, idx, hSign);
+#pragma unroll
+    for (int i = 0; i < M; ++i) c.EV0[i] = c.EV1[i];                  /* :550 */
+    if constexpr (DENSE) {
+        if (c.h != c.h_stage) c.haveB = false;                         /* truncated: rebuild the dense stages (quirk Q6) */
+        remat_bip<METHOD, SYS, FMA>(sys, p, c);
+    }
+    double Xn = c.X, hio = c.h;
+    commit_tail<METHOD, SYS, FMA, true, DENSE>(p, idx, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
+                                               c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B);
+    c.X = Xn; c.h = hio;       /* new X, next step size; new Y in c.Y, new F0 in c.F0old */
+    (void)PS;
+}
+
 /* ===================================================================== */
 template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
 __global__ void __launch_bounds__(FLINT_BLOCK_THREADS, FLINT_MIN_BLOCKS)
@@ -275,12 +357,12 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
     const int m = p.m;
     const bool const_step = p.const_step != 0;
     const double fac = const_step ? 1.0 : kLastStepExpFac;              /* :106-110 */
-    const double SFl = p.szp[0], SFmin = p.szp[1], SFmax = p.szp[2], beta = p.szp[3], beta_mult = p.szp[4];
+    const double SFl = p.szp[0], SFmin = p.szp[1], beta = p.szp[3], beta_mult = p.szp[4];
     const double expo = madd<FMA>(-beta, beta_mult, 1.0 / ((double)METHOD::Q + 1.0));   /* src/StepSz.f90:153 */
 
-    /* per-trajectory state */
+    /* per-trajectory (loop-carried) state */
     long idx = -1;
-    bool have = false, exhausted = false, first = true;
+    bool have = false, exhausted = false, first = true, pending = false;
     double X = 0, h = 0, Xf = 0, hSign = 1, hmax = 0, hbyhoptOld = 0;
     double Y[N], F0[N];
     int total = 0, acc = 0, rej = 0, fcalls = 0, st = FLINT_SUCCESS;
@@ -291,6 +373,7 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
     unsigned evmask = 0;
     int evAction = FLINT_EVENTACTION_CONTINUE, evCount = 0;
     bool eventsOn = false;
+    EvCtx<METHOD, SYS> ctx;                 /* local memory; touched only when an event has to be located */
 #pragma unroll
     for (int i = 0; i < N; ++i) { Y[i] = 0; F0[i] = 0; }
 #pragma unroll
@@ -359,7 +442,14 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         for (int c = 0; c < N; ++c) yy[c] = Y[c];
                         sys.events(p.evset, X, yy, (1u << m) - 1u, EV0, EvDir, 0, da);
                     }
-                    sys.template rhs<FMA>(X, Y, F0);                        /* :224-225 */
+                    {                                                       /* :224-225 */
+                        VecN<N> yv;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) yv.v[c] = Y[c];
+                        const VecN<N> fv = rhs_call<SYS, FMA>(sys, X, yv);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) F0[c] = fv.v[c];
+                    }
                     fcalls = 1;
                     hmax = p.hmax_opt;
                     if (hmax == 0.0) hmax = fabs(Xf - X);                   /* :237 */
@@ -373,12 +463,12 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         const double d0 = norm2<FMA, N>(t0), d1 = norm2<FMA, N>(t1);
                         double h0 = (d0 <= 1.0e-5 || d1 <= 1.0e-5) ? 1.0e-6 : (0.01 * d0) / d1;
                         h0 = hSign * dmin(h0, hmax);
-                        double yh[N], F1[N];
+                        VecN<N> yh;
 #pragma unroll
-                        for (int c = 0; c < N; ++c) yh[c] = madd<FMA>(h0, F0[c], Y[c]);
-                        sys.template rhs<FMA>(X + h0, yh, F1);
+                        for (int c = 0; c < N; ++c) yh.v[c] = madd<FMA>(h0, F0[c], Y[c]);
+                        const VecN<N> F1 = rhs_call<SYS, FMA>(sys, X + h0, yh);
 #pragma unroll
-                        for (int c = 0; c < N; ++c) t0[c] = (F1[c] - F0[c]) / sc0[c];
+                        for (int c = 0; c < N; ++c) t0[c] = (F1.v[c] - F0[c]) / sc0[c];
                         const double d2 = norm2<FMA, N>(t0) / h0;
                         const double dMax = dmax(d1, fabs(d2));
                         double h1;
@@ -399,6 +489,19 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
         }
         if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
+        /* ---------------- deferred: finish an accepted step whose events have to be located ---------------- */
+        if (EVENTS && pending) {
+            deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, hSign);
+            X = ctx.X; h = ctx.h; hbyhoptOld = ctx.hbyhoptOld; lastRej = ctx.lastRej; LAST = ctx.LAST; st = ctx.st;
+            fcalls = ctx.fcalls; evmask = ctx.evmask; evAction = ctx.action; evCount = ctx.evcount;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Y[i] = ctx.Y[i]; F0[i] = ctx.F0old[i]; }
+#pragma unroll
+            for (int i = 0; i < M; ++i) { EV0[i] = ctx.EV0[i]; EvDir[i] = ctx.EvDir[i]; }
+            pending = false;
+            if (!(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
+        }
+
         /* ---------------- one step attempt for every lane that owns a trajectory (:263-637) ---------------- */
         if (have) {
             if (hSign * (madd<FMA>(fac, h, X) - Xf) > 0.0) { h = Xf - X; LAST = true; }   /* :268-271 */
@@ -407,17 +510,11 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
             total += 1;
             double hbyhopt = 1.0;
             if (!const_step) hbyhopt = flint_det_pow(Err, expo);            /* src/StepSz.f90:153 */
-            double hnew;
             if (Err <= 1.0) {                                               /* :283 */
-                double F0new[N], Y1[N];
-#pragma unroll
-                for (int c = 0; c < N; ++c) F0new[c] = ks[METHOD::SLOT_F0NEW][c];
                 fcalls += METHOD::FC_ACC;
                 acc += 1;
                 if (p.step_once) LAST = true;                               /* :289 */
                 bool bip_counted = false;                                   /* BipComputed :292 */
-#pragma unroll
-                for (int c = 0; c < N; ++c) Y1[c] = Ynew[c];
 
                 if (stiffMode == 1 || stiffMode == 2) {                     /* CheckStiffness :299-308, :767-798 */
                     bool stiff = false;
@@ -440,17 +537,15 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                     }
                 }
 
-                double ENY[N];
-                double B[PS + 1][N];       /* dead (never written) unless DENSE */
-                bool haveB = false;
-#pragma unroll
-                for (int c = 0; c < N; ++c) ENY[c] = Y1[c];
+                bool rare = false;
                 if (EVENTS && eventsOn) {                                   /* :313-552 */
-                    double EV1[M];
+                    double EV1[M], yy[N];
 #pragma unroll
                     for (int i = 0; i < M; ++i) EV1[i] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) yy[c] = Ynew[c];
                     int da = 0;
-                    sys.events(p.evset, X + h, ENY, (1u << m) - 1u, EV1, EvDir, 0, da);   /* :324-325 */
+                    sys.events(p.evset, X + h, yy, (1u << m) - 1u, EV1, EvDir, 0, da);   /* :324-325 */
                     unsigned det = 0, ss = 0;
 #pragma unroll
                     for (int i = 0; i < M; ++i) {
@@ -460,88 +555,42 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         }
                     }
                     if (ss && !bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }   /* :337-344, quirk Q1 (lazy) */
-                    if (det || (ss & evmask)) {
-                        EvCtx<METHOD, SYS> c;
-                        c.X = X; c.h = h; c.h_stage = h;
+                    rare = det || (ss & evmask);
+                    if (rare) {            /* stash the step; it is committed at the top of the next lane iteration */
+                        ctx.X = X; ctx.h = h; ctx.h_stage = h;
 #pragma unroll
-                        for (int i = 0; i < N; ++i) { c.Y[i] = Y[i]; c.Y1[i] = Y1[i]; c.F0old[i] = F0[i]; c.ENY[i] = ENY[i]; }
-#pragma unroll
-                        for (int i = 0; i < M; ++i) { c.EV0[i] = EV0[i]; c.EV1[i] = EV1[i]; c.EvDir[i] = EvDir[i]; }
-                        c.evmask = evmask; c.det = det; c.ss = ss; c.action = evAction; c.st = st; c.fcalls = fcalls;
-                        c.evcount = evCount; c.LAST = LAST; c.bip_counted = bip_counted; c.haveB = false;
-                        event_rare_path<METHOD, SYS, FMA>(sys, p, c, idx, hSign);
-                        h = c.h;
-#pragma unroll
-                        for (int i = 0; i < N; ++i) { Y1[i] = c.Y1[i]; ENY[i] = c.ENY[i]; }
-#pragma unroll
-                        for (int i = 0; i < M; ++i) { EV1[i] = c.EV1[i]; EvDir[i] = c.EvDir[i]; }
-                        evmask = c.evmask; evAction = c.action; st = c.st; fcalls = c.fcalls; evCount = c.evcount;
-                        LAST = c.LAST; bip_counted = c.bip_counted;
-                        if constexpr (DENSE) {
-                            if (c.h != c.h_stage) {   /* an action truncated the step: rebuild the dense stages (quirk Q6) */
-                                rare_dense<METHOD, SYS, FMA>(sys, p, c);
-#pragma unroll
-                                for (int j = 0; j <= PS; ++j)
-#pragma unroll
-                                    for (int i = 0; i < N; ++i) B[j][i] = c.B[j][i];
-                                haveB = true;
-                            }
+                        for (int i = 0; i < N; ++i) {
+                            ctx.Y[i] = Y[i]; ctx.Y1[i] = Ynew[i]; ctx.F0old[i] = F0[i]; ctx.ENY[i] = yy[i];
+                            ctx.F0new[i] = ks[METHOD::SLOT_F0NEW][i];
                         }
-                    }
 #pragma unroll
-                    for (int i = 0; i < M; ++i) EV0[i] = EV1[i];            /* :550 */
-                }
-
-                if constexpr (DENSE) {                                      /* :555-566 */
-                    if (!bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }
-                    if (!haveB) METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Y1, B);
-                    if (acc <= p.dense_cap) {
-                        p.dxint[(long)acc * NN + idx] = X + h;
-                        for (int j = 0; j <= PS; ++j)
-                            for (int ii = 0; ii < p.nI; ++ii) {
-                                double v = 0.0;
+                        for (int i = 0; i < M; ++i) { ctx.EV0[i] = EV0[i]; ctx.EV1[i] = EV1[i]; ctx.EvDir[i] = EvDir[i]; }
+                        ctx.evmask = evmask; ctx.det = det; ctx.ss = ss; ctx.action = evAction; ctx.st = st; ctx.fcalls = fcalls;
+                        ctx.evcount = evCount; ctx.LAST = LAST; ctx.bip_counted = bip_counted; ctx.haveB = false;
+                        ctx.Err = Err; ctx.hbyhopt = hbyhopt; ctx.hbyhoptOld = hbyhoptOld; ctx.hmax = hmax; ctx.acc = acc; ctx.lastRej = lastRej;
+                        pending = true;
+                    } else {
 #pragma unroll
-                                for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
-                                p.dbip[(((long)j * p.nI + ii) * p.dense_cap + (acc - 1)) * NN + idx] = v;
-                            }
+                        for (int i = 0; i < M; ++i) EV0[i] = EV1[i];        /* :550 */
                     }
                 }
-
-                if (EVENTS && eventsOn) {                                   /* :572-582 (quirks Q4, Q5) */
-                    const int act = evAction & 0x7f;
-                    if (act == FLINT_EVENTACTION_RESTARTINT) fcalls += 1;
-                    else if (act == FLINT_EVENTACTION_CHANGESOLY) {
-#pragma unroll
-                        for (int c = 0; c < N; ++c) Y1[c] = ENY[c];
-                        fcalls += 1;
-                    }
+                if (!rare) {
+                    double B[PS + 1][N];       /* dead unless DENSE */
+                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Ynew, B);
+                    double hio = h;
+                    commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, eventsOn, evAction, hSign, hmax, X, Y, F0, hio, hbyhoptOld, lastRej, LAST, st,
+                                                                 fcalls, acc, h, Ynew, ks[METHOD::SLOT_F0NEW], Err, hbyhopt, bip_counted, Ynew, B);
+                    h = hio;
                 }
-                if (p.steps_on && acc < p.steps_cap) {                      /* :585-588 */
-                    p.xint[(long)acc * NN + idx] = X + h;
-#pragma unroll
-                    for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + acc) * NN + idx] = Y1[c];
-                }
-                X = X + h;                                                  /* :591-592 */
-#pragma unroll
-                for (int c = 0; c < N; ++c) { Y[c] = Y1[c]; F0[c] = F0new[c]; }
-                if (!const_step) {                                          /* :595-605, src/StepSz.f90:156-168 */
-                    if (beta != 0.0) hbyhopt = hbyhopt / flint_det_pow(hbyhoptOld, beta);
-                    hnew = h * dmin(SFmax, dmax(SFmin, SFl / hbyhopt));
-                    hbyhoptOld = dmax(Err, hbyhoptOld);
-                    if (fabs(hnew) > hmax) hnew = hSign * hmax;
-                    if (lastRej) hnew = hSign * dmin(fabs(hnew), fabs(h));
-                    lastRej = false;
-                } else hnew = h;
             } else {                                                        /* :607-624 */
                 fcalls += METHOD::FC_REJ;
                 if (acc >= 1) rej += 1;
-                hnew = h * dmax(SFmin, SFl / hbyhopt);                      /* src/StepSz.f90:176 */
+                h = h * dmax(SFmin, SFl / hbyhopt);                         /* src/StepSz.f90:176, :627 */
                 lastRej = true;
                 LAST = false;
+                if (!const_step && fabs(h) * 0.01 <= fabs(X) * kEps) st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
             }
-            h = hnew;                                                       /* :627 */
-            if (!const_step && !LAST && fabs(h) * 0.01 <= fabs(X) * kEps) st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
-            if (!(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
+            if (!pending && !(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
         }
     }
 }
