@@ -112,6 +112,8 @@ def lib():
         L.flint_b200_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.flint_b200_launch_count.restype = C.c_long
         L.flint_b200_last_kernel_ms.restype = C.c_double
+        L.flint_b200_selftest_arith.restype = C.c_int
+        L.flint_b200_selftest_arith.argtypes = [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
         _lib = L
     return _lib
 
@@ -426,6 +428,15 @@ def measure_fp64_peak(device=0):
     clk = C.c_double(0)
     tf = lib().flint_b200_measure_fp64_peak(int(device), C.byref(clk))
     return tf, clk.value
+
+
+def selftest_arith(n=1 << 26, seed=12345):
+    """(mismatches, divisions checked, square roots checked) of the div/sqrt helper self-test."""
+    out = (C.c_ulonglong * 3)()
+    st = lib().flint_b200_selftest_arith(int(n), int(seed), out)
+    if st != FLINT_SUCCESS:
+        raise RuntimeError("selftest_arith failed: " + last_error())
+    return int(out[0]), int(out[1]), int(out[2])
 
 
 def launch_count():

@@ -443,12 +443,7 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         sys.events(p.evset, X, yy, (1u << m) - 1u, EV0, EvDir, 0, da);
                     }
                     {                                                       /* :224-225 */
-                        VecN<N> yv;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) yv.v[c] = Y[c];
-                        const VecN<N> fv = rhs_call<SYS, FMA>(sys, X, yv);
-#pragma unroll
-                        for (int c = 0; c < N; ++c) F0[c] = fv.v[c];
+                        rhs_eval<SYS, FMA>(sys, Y, F0);
                     }
                     fcalls = 1;
                     hmax = p.hmax_opt;
@@ -463,12 +458,12 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         const double d0 = norm2<FMA, N>(t0), d1 = norm2<FMA, N>(t1);
                         double h0 = (d0 <= 1.0e-5 || d1 <= 1.0e-5) ? 1.0e-6 : (0.01 * d0) / d1;
                         h0 = hSign * dmin(h0, hmax);
-                        VecN<N> yh;
+                        double yh[N], F1[N];
 #pragma unroll
-                        for (int c = 0; c < N; ++c) yh.v[c] = madd<FMA>(h0, F0[c], Y[c]);
-                        const VecN<N> F1 = rhs_call<SYS, FMA>(sys, X + h0, yh);
+                        for (int c = 0; c < N; ++c) yh[c] = madd<FMA>(h0, F0[c], Y[c]);
+                        rhs_eval<SYS, FMA>(sys, yh, F1);
 #pragma unroll
-                        for (int c = 0; c < N; ++c) t0[c] = (F1.v[c] - F0[c]) / sc0[c];
+                        for (int c = 0; c < N; ++c) t0[c] = (F1[c] - F0[c]) / sc0[c];
                         const double d2 = norm2<FMA, N>(t0) / h0;
                         const double dMax = dmax(d1, fabs(d2));
                         double h1;

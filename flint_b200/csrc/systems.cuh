@@ -10,8 +10,15 @@
  * A system provides:
  *   static constexpr int N       state dimension
  *   static constexpr int M_MAX   largest number of events among its event sets
- *   rhs<FMA>(x, y, f)            F
+ *   F, split into its trivial and its computed part so that the integrator neither marshals nor
+ *   multiplies what it already knows:
+ *     NIN, in_idx(i)             the states the computed part reads
+ *     NOUT                       number of computed derivative components
+ *     fsrc(c)                    f[c] = y[fsrc(c)] if >= 0; +0.0 if -1; out[-2 - fsrc(c)] otherwise
+ *     accel<FMA>(in, out)        the computed components (branch-free division / square root, arith.cuh)
+ *   rhs<FMA>(x, y, f)            F assembled from the above (eval_rhs, below)
  *   events(evset, x, y, eval_bits, value, dir, loc_event, action)   G
+ * All four systems are autonomous (F does not read x).
  * `params` of Integrate(params=...) is forwarded in sp_params (unused by the
  * reference's own systems).
  */
@@ -23,6 +30,38 @@
 
 namespace flint {
 
+/* F assembled from a system's trivial/computed split */
+template <bool FMA, class SYS>
+__device__ __forceinline__ void eval_rhs(const SYS& sys, const double (&y)[SYS::N], double (&f)[SYS::N])
+{
+    double in[SYS::NIN], out[SYS::NOUT];
+#pragma unroll
+    for (int i = 0; i < SYS::NIN; ++i) in[i] = y[SYS::in_idx(i)];
+    sys.template accel<FMA>(in, out);
+#pragma unroll
+    for (int c = 0; c < SYS::N; ++c) {
+        const int src = SYS::fsrc(c);
+        f[c] = src >= 0 ? y[src >= 0 ? src : 0] : (src == -1 ? 0.0 : out[src <= -2 ? -2 - src : 0]);
+    }
+}
+
+/* the four CR3BP quotients with the plain operators (cold path of accel) */
+struct Quot4 { double q[4]; };
+static __device__ __noinline__ Quot4 cr3bp_quotients_plain(double s1, double s2, double u1, double u2, double u3, double u4)
+{
+    const double n1 = sqrt(s1), n2 = sqrt(s2);
+    const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
+    Quot4 r;
+    r.q[0] = u1 / r1c; r.q[1] = u2 / r2c; r.q[2] = u3 / r1c; r.q[3] = u4 / r2c;
+    return r;
+}
+
+static __device__ __noinline__ double twobody_fac_plain(double GM, double s)
+{
+    const double nr = sqrt(s);
+    return -GM / ((nr * nr) * nr);
+}
+
 /* ---- planar CR3BP: tests/test_CR3BP.f90:167-186; events :97-164 and README.md:121-149 ---- */
 struct SysCR3BPPlanar {
     static constexpr int N = 6;
@@ -31,24 +70,36 @@ struct SysCR3BPPlanar {
     double mu, omm;   /* omm = 1 - mu (one rounding, as `1.0_WP-mu` at run time) */
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = 1.0 - mu; }
 
+    static constexpr int NIN = 4, NOUT = 2;
+    __host__ __device__ static constexpr int in_idx(int i) { return i < 2 ? i : i + 1; }          /* y0 y1 y3 y4 */
+    __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : (c == 5 ? -1 : -2 - (c - 3)); }
+
     template <bool FMA>
-    __device__ __forceinline__ void rhs(double /*x*/, const double (&y)[N], double (&f)[N]) const
+    __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
     {
-        const double a = y[0] + mu;
-        const double b = y[0] - omm;
+        const double y0 = in[0], y1 = in[1], y3 = in[2], y4 = in[3];
+        const double a = y0 + mu;
+        const double b = y0 - omm;
         double s1 = __dmul_rn(a, a)   /* == 0 + x*x: x*x is never -0 */;
-        s1 = madd<FMA>(y[1], y[1], s1);
-        const double n1 = sqrt(s1);
-        const double r1c = (n1 * n1) * n1;
-        double s2 = __dmul_rn(b, b)   /* == 0 + x*x: x*x is never -0 */;
-        s2 = madd<FMA>(y[1], y[1], s2);
-        const double n2 = sqrt(s2);
-        const double r2c = (n2 * n2) * n2;
-        f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
-        f[3] = (madd<FMA>(2.0, y[4], y[0]) - (omm * a) / r1c) - (mu * b) / r2c;
-        f[4] = (madd<FMA>(-2.0, y[3], y[1]) - (omm * y[1]) / r1c) - (mu * y[1]) / r2c;
-        f[5] = 0.0;
+        s1 = madd<FMA>(y1, y1, s1);
+        double s2 = __dmul_rn(b, b);
+        s2 = madd<FMA>(y1, y1, s2);
+        const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1;
+        const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4);
+        const double n1 = sqrt_nochk(s1), n2 = sqrt_nochk(s2);
+        const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
+        const double i1 = rcp_newton(r1c), i2 = rcp_newton(r2c);
+        double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
+        double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
+        if (!ok) {                                   /* operands outside the fast-path range: plain operators, out of line */
+            const Quot4 q = cr3bp_quotients_plain(s1, s2, u1, u2, u3, u4);
+            q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3];
+        }
+        out[0] = (madd<FMA>(2.0, y4, y0) - q1) - q2;
+        out[1] = (madd<FMA>(-2.0, y3, y1) - q3) - q4;
     }
+    template <bool FMA>
+    __device__ __forceinline__ void rhs(double /*x*/, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
 
     /* eval_bits: bit i set <=> EvalEvents(i+1) == 1.  loc_event: 1-based located id, 0 = absent. */
     __device__ __forceinline__ void events(int evset, double x, double (&y)[N], unsigned eval_bits,
@@ -87,26 +138,42 @@ struct SysCR3BPSpatial {
     double mu, omm;
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = 1.0 - mu; }
 
+    static constexpr int NIN = 5, NOUT = 3;
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y4 */
+    __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
+
     template <bool FMA>
-    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const
+    __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
     {
-        const double a = y[0] + mu;
-        const double b = y[0] - omm;
+        const double y0 = in[0], y1 = in[1], y2 = in[2], y3 = in[3], y4 = in[4];
+        const double a = y0 + mu;
+        const double b = y0 - omm;
         double s1 = __dmul_rn(a, a)   /* == 0 + x*x: x*x is never -0 */;
-        s1 = madd<FMA>(y[1], y[1], s1);
-        s1 = madd<FMA>(y[2], y[2], s1);
-        const double n1 = sqrt(s1);
-        const double r1c = (n1 * n1) * n1;
-        double s2 = __dmul_rn(b, b)   /* == 0 + x*x: x*x is never -0 */;
-        s2 = madd<FMA>(y[1], y[1], s2);
-        s2 = madd<FMA>(y[2], y[2], s2);
-        const double n2 = sqrt(s2);
-        const double r2c = (n2 * n2) * n2;
-        f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
-        f[3] = (madd<FMA>(2.0, y[4], y[0]) - (omm * a) / r1c) - (mu * b) / r2c;
-        f[4] = (madd<FMA>(-2.0, y[3], y[1]) - (omm * y[1]) / r1c) - (mu * y[1]) / r2c;
-        f[5] = (-omm * y[2]) / r1c - (mu * y[2]) / r2c;
+        s1 = madd<FMA>(y1, y1, s1);
+        s1 = madd<FMA>(y2, y2, s1);
+        double s2 = __dmul_rn(b, b);
+        s2 = madd<FMA>(y1, y1, s2);
+        s2 = madd<FMA>(y2, y2, s2);
+        const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1, u5 = -omm * y2, u6 = mu * y2;
+        const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4) & moderate(u5) &
+                        moderate(u6);
+        const double n1 = sqrt_nochk(s1), n2 = sqrt_nochk(s2);
+        const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
+        const double i1 = rcp_newton(r1c), i2 = rcp_newton(r2c);
+        double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
+        double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
+        double q5 = div_rcp_nochk(u5, r1c, i1), q6 = div_rcp_nochk(u6, r2c, i2);
+        if (!ok) {                                   /* operands outside the fast-path range: plain operators, out of line */
+            const Quot4 q = cr3bp_quotients_plain(s1, s2, u1, u2, u3, u4);
+            const Quot4 z = cr3bp_quotients_plain(s1, s2, u5, u6, u5, u6);
+            q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3]; q5 = z.q[0]; q6 = z.q[1];
+        }
+        out[0] = (madd<FMA>(2.0, y4, y0) - q1) - q2;
+        out[1] = (madd<FMA>(-2.0, y3, y1) - q3) - q4;
+        out[2] = q5 - q6;
     }
+    template <bool FMA>
+    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&)[N], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
 };
 
@@ -118,13 +185,19 @@ struct SysLorenz {
     double sigma, rho, beta;
     __device__ __forceinline__ void load(const double* sp) { sigma = sp[0]; rho = sp[1]; beta = sp[2]; }
 
+    static constexpr int NIN = 3, NOUT = 3;
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }
+    __host__ __device__ static constexpr int fsrc(int c) { return -2 - c; }
+
     template <bool FMA>
-    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const
+    __device__ __forceinline__ void accel(const double (&y)[NIN], double (&f)[NOUT]) const
     {
         f[0] = sigma * (y[1] - y[0]);
         f[1] = __dsub_rn(__dmul_rn(y[0], rho - y[2]), y[1]);   /* never fused, in both modes */
         f[2] = madd<FMA>(y[0], y[1], -(beta * y[2]));
     }
+    template <bool FMA>
+    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&)[N], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
 };
 
@@ -136,17 +209,25 @@ struct SysTwoBody {
     double GM;
     __device__ __forceinline__ void load(const double* sp) { GM = sp[0]; }
 
+    static constexpr int NIN = 3, NOUT = 3;
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* position */
+    __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
+
     template <bool FMA>
-    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const
+    __device__ __forceinline__ void accel(const double (&y)[NIN], double (&f)[NOUT]) const
     {
         double s = __dmul_rn(y[0], y[0])   /* == 0 + x*x: x*x is never -0 */;
         s = madd<FMA>(y[1], y[1], s);
         s = madd<FMA>(y[2], y[2], s);
-        const double nr = sqrt(s);
-        const double fac = -GM / ((nr * nr) * nr);
-        f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
-        f[3] = fac * y[0]; f[4] = fac * y[1]; f[5] = fac * y[2];
+        const bool ok = moderate_sq(s) & moderate(GM);
+        const double nr = sqrt_nochk(s);
+        const double d = (nr * nr) * nr;
+        double fac = div_rcp_nochk(-GM, d, rcp_newton(d));
+        if (!ok) fac = twobody_fac_plain(GM, s);
+        f[0] = fac * y[0]; f[1] = fac * y[1]; f[2] = fac * y[2];
     }
+    template <bool FMA>
+    __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&y)[N], unsigned eval_bits, double (&value)[M_MAX],
                                            int (&dir)[M_MAX], int loc_event, int& action) const
     {

@@ -194,6 +194,11 @@ double flint_b200_measure_fp64_peak(int device, double* sm_clock_mhz_out);
 long flint_b200_launch_count(void);
 /* Last integrate kernel's duration in ms measured with CUDA events on the launch stream (batch calls). */
 double flint_b200_last_kernel_ms(void);
+/* Device self-test of the branch-free division / square-root helpers the right-hand sides use
+ * (csrc/arith.cuh): n operand sets drawn from `seed`; result3 = {results that differ from the plain
+ * IEEE operator although the helper's range test passed (must be 0), divisions that passed the range
+ * test, square roots that passed}.  Returns FLINT_SUCCESS or FLINT_ERROR. */
+int flint_b200_selftest_arith(long n, unsigned long long seed, unsigned long long* result3);
 
 #ifdef __cplusplus
 }

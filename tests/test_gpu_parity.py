@@ -15,6 +15,16 @@ METHODS = [F.ERK_DOP853, F.ERK_DOP54, F.ERK_VERNER98R, F.ERK_VERNER65E]
 MNAME = {17: "DOP853", 18: "DOP54", 19: "Verner98R", 20: "Verner65E"}
 
 
+def test_div_sqrt_helpers_equal_ieee_operators():
+    """The right-hand sides and error norms use branch-free division / square root (csrc/arith.cuh)
+    that must equal `/` and `sqrt` bit for bit wherever their range test passes: 2^28 operand sets
+    (every exponent, NaN/Inf/subnormals, physical magnitudes, zero numerators), two seeds."""
+    for seed in (12345, 987654321):
+        bad, ndiv, nsqrt = F.selftest_arith(1 << 28, seed)
+        assert bad == 0
+        assert ndiv > (1 << 27) and nsqrt > (1 << 27)      # the range test is not vacuous
+
+
 @pytest.mark.parametrize("arith", [F.FLINT_ARITH_STRICT, F.FLINT_ARITH_FMA])
 def test_config3_northstar_parity(arith):
     """Config 3a (the metric's configuration) on 4096 seeded orbits."""

@@ -182,20 +182,31 @@ class Plan:
 
 
 def emit_sum(E, terms, lead_zero, keep_zero_terms=False, var="acc"):
+    """var = sum of k_j[c] * coef_j, left to right (from 0.0 when lead_zero).  For a component whose
+    derivative is structurally +0.0 (SYS::fsrc(c) == -1) every product is +-0, so the sum is a zero whose
+    sign is known here: -0.0 iff the sum does not start from 0.0 and every coefficient is negative
+    ((-0) + (-0) = -0, anything else rounds to +0).  The branch folds after unrolling."""
+    used = [(k, c) for k, c in terms if c != 0.0 or keep_zero_terms]
+    if not used:
+        E("double %s = 0.0;" % var)
+        return
+    zsign = "-0.0" if (not lead_zero and all(c < 0.0 for _, c in used)) else "0.0"
+    E("double %s;" % var)
+    E("if (SYS::fsrc(c) == -1) %s = %s;" % (var, zsign))
+    E("else {")
+    E.ind += 1
     first = True
-    for kexpr, coef in terms:
-        if coef == 0.0 and not keep_zero_terms:
-            continue
+    for kexpr, coef in used:
         if first:
             if lead_zero:
-                E("double %s = madd<FMA>(%s, %s, 0.0);" % (var, kexpr, cx(coef)))
+                E("%s = madd<FMA>(%s, %s, 0.0);" % (var, kexpr, cx(coef)))
             else:
-                E("double %s = __dmul_rn(%s, %s);" % (var, kexpr, cx(coef)))
+                E("%s = __dmul_rn(%s, %s);" % (var, kexpr, cx(coef)))
             first = False
         else:
             E("%s = madd<FMA>(%s, %s, %s);" % (var, kexpr, cx(coef), var))
-    if first:
-        E("double %s = 0.0;" % var)
+    E.ind -= 1
+    E("}")
 
 
 def stage_sums(E, P, row, dest, lead_zero, keep_zero_terms=False, save_sum=None, hname="h"):
@@ -215,43 +226,65 @@ SC_BLOCK = ["double sc[N];", "#pragma unroll", "for (int c = 0; c < N; ++c)",
 
 
 def emit_error(E, P):
-    """error norm into Err (estimate == true path)"""
+    """error norm into Err (estimate == true path).  The n (DOP853: 2n) quotients by Sc are formed with
+    one refined reciprocal per component and no branches (arith.cuh: div_rcp_z); a failed range test
+    redoes them with the plain operator out of line."""
     M = P.M
     for ln in SC_BLOCK:
         E(ln)
+    E("double isc[N];")
+    E("#pragma unroll")
+    E("for (int c = 0; c < N; ++c) isc[c] = rcp_newton(sc[c]);")
+    E("bool qok = true;")
     if M == "DOP853":
-        E("double Es = 0.0, E3 = 0.0;")
+        E("VecN<N> t5, t3;")
         E("#pragma unroll")
         E("for (int c = 0; c < N; ++c) {")
         E.ind += 1
         emit_sum(E, [(P.k(j + 1), P.e[j]) for j in range(P.sint)], lead_zero=False, var="t")
-        E("const double q = t / sc[c];")
-        E("Es = (c == 0) ? __dmul_rn(q, q) : madd<FMA>(q, q, Es);")
+        E("t5.v[c] = t;")
+        E("double u = madd<FMA>(%s, %s, bsum[c]);" % (cx(-P.bhh[0]), P.k(1)))
+        E("u = madd<FMA>(%s, %s, u);" % (cx(-P.bhh[1]), P.k(9)))
+        E("u = madd<FMA>(%s, %s, u);" % (cx(-P.bhh[2]), P.k(12)))
+        E("t3.v[c] = u;")
         E.ind -= 1
         E("}")
+        E("VecN<N> q5, q3;")
         E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) {")
-        E.ind += 1
-        E("double t = madd<FMA>(%s, %s, bsum[c]);" % (cx(-P.bhh[0]), P.k(1)))
-        E("t = madd<FMA>(%s, %s, t);" % (cx(-P.bhh[1]), P.k(9)))
-        E("t = madd<FMA>(%s, %s, t);" % (cx(-P.bhh[2]), P.k(12)))
-        E("const double q = t / sc[c];")
-        E("E3 = (c == 0) ? __dmul_rn(q, q) : madd<FMA>(q, q, E3);")
-        E.ind -= 1
+        E("for (int c = 0; c < N; ++c) { q5.v[c] = div_rcp_z(t5.v[c], sc[c], isc[c], qok); q3.v[c] = div_rcp_z(t3.v[c], sc[c], isc[c], qok); }")
+        E("if (!qok) {")
+        E("    VecN<N> scv;")
+        E("#pragma unroll")
+        E("    for (int c = 0; c < N; ++c) scv.v[c] = sc[c];")
+        E("    q5 = quotients_plain<N>(t5, scv); q3 = quotients_plain<N>(t3, scv);")
         E("}")
+        E("double Es = 0.0, E3 = 0.0;")
+        E("#pragma unroll")
+        E("for (int c = 0; c < N; ++c) Es = (c == 0) ? __dmul_rn(q5.v[c], q5.v[c]) : madd<FMA>(q5.v[c], q5.v[c], Es);")
+        E("#pragma unroll")
+        E("for (int c = 0; c < N; ++c) E3 = (c == 0) ? __dmul_rn(q3.v[c], q3.v[c]) : madd<FMA>(q3.v[c], q3.v[c], E3);")
         E("double den = madd<FMA>(0.01, E3, Es);")
         E("if (den == 0.0) den = 1.0;")
         E("Err = (fabs(h) * Es) * sqrt(1.0 / ((double)N * den));")
     else:
-        E("double sm = 0.0;")
+        E("VecN<N> tn, qn;")
         E("#pragma unroll")
         E("for (int c = 0; c < N; ++c) {")
         E.ind += 1
         emit_sum(E, [(P.k(j + 1), P.e[j]) for j in range(P.sint)], lead_zero=P.generic, var="t")
-        E("const double q = (h * t) / sc[c];")
-        E("sm = (c == 0) ? __dmul_rn(q, q) : madd<FMA>(q, q, sm);")
+        E("tn.v[c] = h * t;")
+        E("qn.v[c] = div_rcp_z(tn.v[c], sc[c], isc[c], qok);")
         E.ind -= 1
         E("}")
+        E("if (!qok) {")
+        E("    VecN<N> scv;")
+        E("#pragma unroll")
+        E("    for (int c = 0; c < N; ++c) scv.v[c] = sc[c];")
+        E("    qn = quotients_plain<N>(tn, scv);")
+        E("}")
+        E("double sm = 0.0;")
+        E("#pragma unroll")
+        E("for (int c = 0; c < N; ++c) sm = (c == 0) ? __dmul_rn(qn.v[c], qn.v[c]) : madd<FMA>(qn.v[c], qn.v[c], sm);")
         E("Err = sqrt(sm / (double)N);")
 
 
@@ -372,12 +405,7 @@ def gen_method(E_out, S, M):
             E("{   /* %s */" % (("stage %d" % st) if kind == "stage" else "evaluation at (X0+h, Ynew)"))
             E.ind += 1
             emit_iteration_pre(E, P, it, kind, st)
-            E("VecN<N> yv;")
-            E("#pragma unroll")
-            E("for (int c = 0; c < N; ++c) yv.v[c] = yt[c];")
-            E("const VecN<N> fv = rhs_call<SYS, FMA>(sys, xs, yv);")
-            E("#pragma unroll")
-            E("for (int c = 0; c < N; ++c) ks[%d][c] = fv.v[c];" % P.slot[st])
+            E("rhs_eval<SYS, FMA>(sys, yt, ks[%d]);" % P.slot[st])
             E.ind -= 1
             E("}")
         if len(P.its) > P.n_int:
