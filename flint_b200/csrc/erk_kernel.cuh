@@ -123,8 +123,8 @@ __device__ __forceinline__ void remat_bip(const SYS& sys, const KArgs& p, EvCtx<
     if (c.haveB) return;
     constexpr int N = SYS::N;
     double ks[METHOD::NSLOT][N], Yn[N], Yp[N], e;
-    METHOD::template step<SYS, FMA, true>(sys, c.X, c.Y, c.F0old, c.h_stage, c.h, ks, Yn, Yp, p.tol, false, e);
-    METHOD::template dense_coeffs<SYS, FMA>(ks, c.Y, c.h, c.Y1, c.B);
+    METHOD::template step<SYS, FMA, true>(sys, c.X, c.Y, c.F0old, c.h_stage, c.h, ks, Yn, Yp, p.tol, false, e, p.coef);
+    METHOD::template dense_coeffs<SYS, FMA>(ks, c.Y, c.h, c.Y1, c.B, p.coef);
     c.haveB = true;
 }
 template <class METHOD, class SYS, bool FMA>
@@ -501,7 +501,7 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
         if (have) {
             if (hSign * (madd<FMA>(fac, h, X) - Xf) > 0.0) { h = Xf - X; LAST = true; }   /* :268-271 */
             double ks[METHOD::NSLOT][N], Ynew[N], Ypre[N], Err;
-            METHOD::template step<SYS, FMA, DENSE>(sys, X, Y, F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err);   /* :274 */
+            METHOD::template step<SYS, FMA, DENSE>(sys, X, Y, F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
             total += 1;
             double hbyhopt = 1.0;
             if (!const_step) hbyhopt = flint_det_pow(Err, expo);            /* src/StepSz.f90:153 */
@@ -571,7 +571,7 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                 }
                 if (!rare) {
                     double B[PS + 1][N];       /* dead unless DENSE */
-                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Ynew, B);
+                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Ynew, B, p.coef);
                     double hio = h;
                     commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, eventsOn, evAction, hSign, hmax, X, Y, F0, hio, hbyhoptOld, lastRej, LAST, st,
                                                                  fcalls, acc, h, Ynew, ks[METHOD::SLOT_F0NEW], Err, hbyhopt, bip_counted, Ynew, B);
@@ -595,7 +595,9 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
 template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
 cudaError_t launch_erk(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    erk_integrate_kernel<METHOD, SYS, FMA, EVENTS, DENSE><<<grid, block, 0, s>>>(a);
+    KArgs b = a;
+    METHOD::load_coefficients(b.coef);
+    erk_integrate_kernel<METHOD, SYS, FMA, EVENTS, DENSE><<<grid, block, 0, s>>>(b);
     return cudaGetLastError();
 }
 template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>

@@ -14,6 +14,8 @@
 #define FLINT_DEFAULT_BLOCK FLINT_BLOCK_THREADS
 #define FLINT_MAX_BLOCK FLINT_BLOCK_THREADS
 
+#define FLINT_NCOEF 256                /* capacity of KArgs::coef (largest pool: Verner98R, 254 values) */
+
 namespace flint {
 
 /* ATol/RTol as Init stores them (scalar or per-component; src/ERKInit.f90:76-87) */
@@ -55,6 +57,7 @@ struct KArgs {
     int steps_on; long steps_cap; double* xint; double* yint; int* steps_count;   /* IntStepsOn output */
     long dense_cap; double* dxint; double* dbip; int* dense_count; int nI; int istates[FLINT_MAX_N];   /* InterpOn storage */
     unsigned long long* work_counter;
+    double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by launch_erk) */
 };
 
 struct InterpArgs {

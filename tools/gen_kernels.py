@@ -46,9 +46,12 @@ def aidx(i, j):
 
 
 class ConstPool:
-    """Coefficients live in `static __constant__` arrays so that every DFMA/DMUL takes its
-    coefficient as a constant-bank operand (c[3][off]); as literals nvcc materialises each
-    64-bit immediate with two UMOVs, which costs ~25 % more instructions in the hot loop."""
+    """Coefficients travel in the KERNEL PARAMETER block (KArgs::coef, constant bank 0), so every
+    DFMA/DMUL takes its coefficient as a c[0x0][off] operand.  Two alternatives were measured and
+    dropped: literals (nvcc materialises each 64-bit immediate with two UMOVs, ~25 % more instructions)
+    and `__constant__` arrays (the optimiser hoists those loads out of the lane loop as loop
+    invariants and ptxas then SPILLS the coefficients to local memory: 12 % of all stall samples sat
+    on the reloads, profiles/r01_notes.md).  The host copies kCH_<method> into KArgs::coef at launch."""
 
     def __init__(self, name):
         self.name, self.vals, self.index = name, [], {}
@@ -58,11 +61,11 @@ class ConstPool:
         if key not in self.index:
             self.index[key] = len(self.vals)
             self.vals.append(float(v))
-        return "%s[%d]" % (self.name, self.index[key])
+        return "C[%d]" % self.index[key]
 
     def decl(self):
         body = ",\n    ".join(", ".join(hx(v) for v in self.vals[i:i + 4]) for i in range(0, len(self.vals), 4))
-        return "static __constant__ double %s[%d] = {\n    %s\n};\n" % (self.name, len(self.vals), body)
+        return "static const double %s[%d] = {\n    %s\n};\n" % (self.name, len(self.vals), body)
 
 
 POOL = None
@@ -342,7 +345,7 @@ def emit_iteration_pre(E, P, it, kind, st):
 
 def gen_method(E_out, S, M):
     global POOL
-    POOL = ConstPool("kC_%s" % M)
+    POOL = ConstPool("kCH_%s" % M)
     E = Emit()
     P = Plan(S, M)
     p = M.lower()
@@ -373,6 +376,8 @@ def gen_method(E_out, S, M):
     E("static constexpr int SLOT_KSINT = %d, SLOT_KSINT_M1 = %d;   /* CheckStiffness operands */" % (P.slot[sint], P.slot[sint - 1]))
     f0new_stage = {"DOP853": 13, "DOP54": 7, "Verner65E": sint, "Verner98R": 0}[M]
     E("static constexpr int SLOT_F0NEW = %d;" % P.slot[f0new_stage])
+    E("static constexpr int NCOEF = NCOEF_%s;" % M)
+    E("static void load_coefficients(double (&dst)[FLINT_NCOEF]) { for (int i = 0; i < NCOEF; ++i) dst[i] = kCH_%s[i]; }" % M)
     E()
     # ------------------------------------------------------------------ step
     E("/* One step attempt (and, DENSE, the extra dense-output stages).  F0 = derivative at (X0,Y0).")
@@ -384,7 +389,7 @@ def gen_method(E_out, S, M):
     E("template <class SYS, bool FMA, bool DENSE>")
     E("static __device__ __forceinline__ void step(const SYS& sys, double X0, const double (&Y0)[SYS::N], const double (&F0)[SYS::N],")
     E("        double h, double hd, double (&ks)[NSLOT][SYS::N], double (&Ynew)[SYS::N], double (&Ypre)[SYS::N], const Tol& tol,")
-    E("        bool estimate, double& Err)")
+    E("        bool estimate, double& Err, const double (&C)[FLINT_NCOEF])")
     E("{")
     E.ind += 1
     E("constexpr int N = SYS::N;")
@@ -453,7 +458,7 @@ def gen_method(E_out, S, M):
     E("/* Dense-output coefficients B[j][c] of theta^j, j = 0..PSTAR (all n states), from the stage vectors. */")
     E("template <class SYS, bool FMA>")
     E("static __device__ __forceinline__ void dense_coeffs(const double (&ks)[NSLOT][SYS::N], const double (&Y0)[SYS::N], double h,")
-    E("        const double (&Y1)[SYS::N], double (&B)[PSTAR + 1][SYS::N])")
+    E("        const double (&Y1)[SYS::N], double (&B)[PSTAR + 1][SYS::N], const double (&C)[FLINT_NCOEF])")
     E("{")
     E.ind += 1
     E("constexpr int N = SYS::N;")
@@ -498,8 +503,10 @@ def gen_method(E_out, S, M):
     E.ind -= 1
     E("};")
     E()
-    E_out.lines.append("/* coefficients of %s in constant memory (deduplicated values) */" % M)
+    E_out.lines.append("/* coefficients of %s (deduplicated values; copied into KArgs::coef at launch) */" % M)
     E_out.lines.extend(POOL.decl().rstrip("\n").split("\n"))
+    E_out.lines.append("constexpr int NCOEF_%s = %d;" % (M, len(POOL.vals)))
+    E_out.lines.append("static_assert(NCOEF_%s <= FLINT_NCOEF, \"KArgs::coef too small\");" % M)
     E_out.lines.extend(E.lines)
 
 
