@@ -36,6 +36,13 @@ struct flint_sys {
     double sp[8];
 };
 
+struct Workspace {                     /* trajectory state block + work lists of Integrate; grows, never shrinks */
+    int device = -1;
+    size_t bytes = 0;
+    void* ptr = nullptr;
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; device = -1; }
+};
+
 struct DenseStore {                    /* device-resident Xint / Bip of the last Integrate with InterpOn */
     int device = -1;
     long N = 0, cap = 0;
@@ -74,6 +81,7 @@ struct flint_erk {
     double Y0[FLINT_MAX_N]{}, Yf[FLINT_MAX_N]{};
     /* dense storage */
     DenseStore dense;
+    Workspace ws;
     bool dense_is_scalar = false;
     bool dense_allocated = false;      /* allocated(me%Xint) */
 };
@@ -135,6 +143,7 @@ extern "C" void flint_erk_destroy(flint_erk_t* e)
 {
     if (!e) return;
     e->dense.release();
+    e->ws.release();
     delete e;
 }
 
@@ -239,7 +248,7 @@ struct DevBuf {                        /* RAII device scratch for FLINT_MEM_HOST
 
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
-    long dense_cap = 0; int block = 0, blocks_per_sm = 0;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0;
 };
 
 }  // namespace
@@ -362,30 +371,101 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         a.dense_cap = cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dense_count = D.dcount;
         me->dense_is_scalar = scalar_call;
     }
-    /* ---- work distribution: persistent lanes ---- */
+    /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
+    ke->load_coefficients(a.coef);
+    {
+        const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = szN * 4;
+        const size_t need_b = sd_b + si_b + 2 * li_b + 64;
+        Workspace& W = me->ws;
+        if (W.device != ex.device || W.bytes < need_b) {
+            W.release();
+            if (cudaMalloc(&W.ptr, need_b) != cudaSuccess) { cudaGetLastError(); return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed (trajectory state)"); }
+            W.bytes = need_b; W.device = ex.device;
+        }
+        char* base = (char*)W.ptr;
+        a.sd = (double*)base; a.si = (int*)(base + sd_b); a.scap = N;
+    }
+    int* listA = (int*)((char*)me->ws.ptr + szN * (size_t)ke->n_state_doubles * 8 + szN * (size_t)ke->n_state_ints * 4);
+    int* listB = listA + szN;
+    unsigned long long* ctr = (unsigned long long*)(listB + szN + ((szN & 1) ? 1 : 0));   /* 8-byte aligned: [0] work, [1] |A|, [2] |B| */
+
+    /* events that are located on (nearly) every step keep the in-loop handling; otherwise park + batch */
+    bool park = events_on && ke->step_park && ke->event;
+    if (park)
+        for (int i = 0; i < m; ++i)
+            if (((evmask >> i) & 1u) && me->ev_stepsz[i] != 0.0) park = false;
+    if (ex.event_mode == 1) park = false;
+    if (ex.event_mode == 2 && events_on && ke->step_park) park = true;
+
+    /* persistent lanes: one resident wave, SM count x resident CTAs */
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ex.device);
     int block = ex.block > 0 ? ex.block : FLINT_DEFAULT_BLOCK;
     block = (block + 31) / 32 * 32;
     if (block > FLINT_MAX_BLOCK) block = FLINT_MAX_BLOCK;
     int bps = 0;
-    if (!cuda_ok(ke->occupancy(&bps, block), "occupancy query")) return me->status = FLINT_ERROR;
+    if (!cuda_ok((park ? ke->occupancy_park : ke->occupancy)(&bps, block), "occupancy query")) return me->status = FLINT_ERROR;
     if (bps < 1) bps = 1;
     if (ex.blocks_per_sm > 0 && ex.blocks_per_sm < bps) bps = ex.blocks_per_sm;
-    long grid = (long)dev_sms * bps;                         /* one resident wave: SM count x resident CTAs */
+    long grid = (long)dev_sms * bps;
     const long need = (N + block - 1) / block;
     if (grid > need) grid = need;
-    unsigned long long* d_counter = scratch.alloc<unsigned long long>(1);
-    if (!d_counter) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
     const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
-    if (!cuda_ok(cudaMemcpyAsync(d_counter, &first_free, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) return me->status = FLINT_ERROR;
-    a.work_counter = d_counter;
+    const unsigned long long ctr0[3] = {first_free, 0ULL, 0ULL};
+    if (!cuda_ok(cudaMemcpyAsync(ctr, ctr0, sizeof ctr0, cudaMemcpyHostToDevice, s), "H2D work counters")) return me->status = FLINT_ERROR;
+    a.work_counter = ctr; a.counter_reset = first_free;
+    const int grid_all = (int)((N + 127) / 128);
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool timed = !ex.async;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-    cudaError_t le = ke->launch(a, (int)grid, block, s);
+    cudaError_t le = ke->init(a, grid_all, 128, s);
     g_launches += 1;
+    if (le == cudaSuccess && !park) {
+        a.list_in = nullptr; a.n_in = nullptr; a.list_out = nullptr; a.n_out = nullptr;
+        le = ke->step(a, (int)grid, block, s);
+        g_launches += 1;
+    } else if (le == cudaSuccess) {
+        /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
+         * parked count and stop when it is zero; asynchronous calls run a fixed schedule (empty kernels return
+         * at once).  The last round resumes with in-loop event handling, so it always finishes. */
+        const int max_rounds = ex.async ? 3 : 64;
+        int cur = 1;                                               /* index of the counter of the list being filled */
+        a.list_in = nullptr; a.n_in = nullptr; a.list_out = listA; a.n_out = ctr + 1;
+        le = ke->step_park(a, (int)grid, block, s);
+        g_launches += 1;
+        for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
+            long n_parked = N;
+            if (!ex.async) {
+                unsigned long long c = 0;
+                if (!cuda_ok(cudaMemcpyAsync(&c, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
+                    !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
+                n_parked = (long)c;
+                if (n_parked == 0) break;
+            }
+            int* lcur = cur == 1 ? listA : listB;
+            int* loth = cur == 1 ? listB : listA;
+            const int oth = cur == 1 ? 2 : 1;
+            a.list_in = lcur; a.n_in = ctr + cur; a.list_out = loth; a.n_out = ctr + oth;
+            le = ke->event(a, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
+            g_launches += 1;
+            if (le != cudaSuccess) break;
+            long g2 = grid;
+            const long need2 = (n_parked + block - 1) / block;
+            if (!ex.async && g2 > need2) {
+                /* fewer lanes than the first wave assumed: hand out every item through the counter instead */
+                g2 = need2 < 1 ? 1 : need2;
+            }
+            if (g2 != grid) {
+                const unsigned long long ff = (unsigned long long)g2 * (unsigned long long)block;
+                if (!cuda_ok(cudaMemcpyAsync(ctr, &ff, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) { le = cudaErrorUnknown; break; }
+            }
+            const bool last = round == max_rounds - 1;
+            le = (last ? ke->step : ke->step_park)(a, (int)g2, block, s);
+            g_launches += 1;
+            cur = oth;
+        }
+    }
     if (timed) cudaEventRecord(e1, s);
     if (!cuda_ok(le, "kernel launch")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
 
@@ -425,6 +505,7 @@ static ExecCtx make_exec(const flint_exec* x)
     if (x) {
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
+        e.event_mode = x->event_mode;
     }
     return e;
 }

@@ -1,7 +1,26 @@
-/* erk_kernel.cuh -- the ensemble integrator kernel (one trajectory per thread).
+/* erk_kernel.cuh -- the ensemble integrator kernels (one trajectory per thread).
  *
  * Device restatement of ERK_class%Integrate (src/ERKIntegrate.f90:29-802) for N
- * independent trajectories.  B200-first structure, not the reference's loop nest:
+ * independent trajectories.  B200-first structure, not the reference's loop nest.  The driver is
+ * THREE kernels around a per-trajectory state block in HBM (TrajState, SoA over trajectories):
+ *
+ *    erk_init_kernel    one thread per trajectory: argument checks, F0, StepSz0Hairer, first event
+ *                       values (:204-259)  ->  state block
+ *    erk_step_kernel    the hot loop: persistent lanes load a trajectory from the state block and
+ *                       step it until it finishes (results stored) or -- EVMODE 2 -- until a step
+ *                       with an event to locate, which is PARKED: step data to the state block,
+ *                       index appended to a list, the lane takes the next trajectory
+ *    erk_event_kernel   one thread per parked trajectory: sub-step scan, Brent, actions, commit of
+ *                       the step  ->  state block; the next erk_step_kernel pass resumes them
+ *
+ * Why: everything that one lane does alone costs 32 lanes.  Measured on the single-kernel version
+ * (profiles/r01_notes.md): 7.5 % of the warp instructions ran with < 8 active lanes (event location
+ * and per-trajectory initialisation inside the lane loop) and took 14 % of the time, and every such
+ * excursion pushed ~100 KB of rare code through the 32 KB instruction cache of an SM whose 16 warps
+ * share it (no_instruction stalls 3.1 vs 0.8 cycles per issue without events).  Batched by kind, the
+ * rare work runs converged and the hot kernel holds only the step loop.  EVMODE 1 keeps the
+ * in-loop event handling for configurations that locate events on (nearly) every step (unmasked
+ * events with an EventStepSz), where parking would advance one step per pass.
  *
  *  * persistent lanes: a thread owns one trajectory at a time; when it finishes it
  *    pulls the next index from a global counter, so lanes whose trajectories need
@@ -344,176 +363,281 @@ __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& 
     (void)PS;
 }
 
-/* ===================================================================== */
-template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
+/* ===================================================================== trajectory state block */
+/* Everything a trajectory carries from one step to the next, plus (parked trajectories) the data of
+ * the accepted step whose events are to be located.  SoA: field f of trajectory i is at [f * cap + i]. */
+template <int N, int M> struct SD {            /* double fields */
+    static constexpr int X = 0, H = 1, HMAX = 2, HOLD = 3, Y = 4, F0 = 4 + N, EV0 = 4 + 2 * N,
+                         HSTEP = 4 + 2 * N + M, Y1 = HSTEP + 1, F0N = Y1 + N, EV1 = F0N + N, ERR = EV1 + M, HBH = ERR + 1,
+                         X0 = HBH + 1, COUNT = X0 + 1;
+};
+struct SI {                                    /* int fields */
+    static constexpr int TOTAL = 0, ACC = 1, REJ = 2, FC = 3, ST = 4, FLAGS = 5, STIFF = 6, EVP = 7, EVC = 8, DET = 9, SS = 10, COUNT = 11;
+};
+constexpr int kFlagLast = 1, kFlagLastRej = 2, kFlagEventsOn = 4, kFlagDone = 8, kFlagBipCounted = 16;
+
+/* the loop-carried state of one trajectory, in registers */
+template <class SYS> struct Lane {
+    static constexpr int N = SYS::N, M = SYS::M_MAX;
+    double X, h, Xf, hSign, hmax, hbyhoptOld;
+    double Y[N], F0[N], EV0[M];
+    int total, acc, rej, fcalls, st;
+    bool LAST, lastRej, eventsOn;
+    int stiffMode, stiffThr, nonStiffThr, stiffOut;
+    int EvDir[M];
+    unsigned evmask;
+    int evAction, evCount;
+};
+
+template <class SYS>
+__device__ __forceinline__ void state_store(const KArgs& p, long idx, const Lane<SYS>& L, int extra_flags)
+{
+    constexpr int N = SYS::N, M = SYS::M_MAX;
+    using D = SD<N, M>;
+    const long c = p.scap;
+    double* d = p.sd + idx;
+    int* q = p.si + idx;
+    d[D::X * c] = L.X; d[D::H * c] = L.h; d[D::HMAX * c] = L.hmax; d[D::HOLD * c] = L.hbyhoptOld;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { d[(D::Y + i) * c] = L.Y[i]; d[(D::F0 + i) * c] = L.F0[i]; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) d[(D::EV0 + i) * c] = L.EV0[i];
+    q[SI::TOTAL * c] = L.total; q[SI::ACC * c] = L.acc; q[SI::REJ * c] = L.rej; q[SI::FC * c] = L.fcalls; q[SI::ST * c] = L.st;
+    q[SI::FLAGS * c] = (L.LAST ? kFlagLast : 0) | (L.lastRej ? kFlagLastRej : 0) | (L.eventsOn ? kFlagEventsOn : 0) | extra_flags;
+    q[SI::STIFF * c] = (L.stiffMode & 3) | ((L.stiffOut + 1) << 2) | (L.stiffThr << 4) | (L.nonStiffThr << 8);
+    int evp = (int)(L.evmask & 0xffu) | ((L.evAction & 0xff) << 8);
+#pragma unroll
+    for (int i = 0; i < M; ++i) evp |= ((L.EvDir[i] + 1) & 3) << (16 + 2 * i);
+    q[SI::EVP * c] = evp; q[SI::EVC * c] = L.evCount;
+}
+/* returns the flags word */
+template <class SYS>
+__device__ __forceinline__ int state_load(const KArgs& p, long idx, Lane<SYS>& L)
+{
+    constexpr int N = SYS::N, M = SYS::M_MAX;
+    using D = SD<N, M>;
+    const long c = p.scap;
+    const double* d = p.sd + idx;
+    const int* q = p.si + idx;
+    const int flags = q[SI::FLAGS * c];
+    L.X = d[D::X * c]; L.h = d[D::H * c]; L.hmax = d[D::HMAX * c]; L.hbyhoptOld = d[D::HOLD * c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { L.Y[i] = d[(D::Y + i) * c]; L.F0[i] = d[(D::F0 + i) * c]; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) L.EV0[i] = d[(D::EV0 + i) * c];
+    L.Xf = p.xf[idx];
+    L.hSign = sign1(L.Xf - d[D::X0 * c]);                                /* :94 */
+    L.total = q[SI::TOTAL * c]; L.acc = q[SI::ACC * c]; L.rej = q[SI::REJ * c]; L.fcalls = q[SI::FC * c]; L.st = q[SI::ST * c];
+    L.LAST = (flags & kFlagLast) != 0; L.lastRej = (flags & kFlagLastRej) != 0; L.eventsOn = (flags & kFlagEventsOn) != 0;
+    const int sf = q[SI::STIFF * c];
+    L.stiffMode = sf & 3; L.stiffOut = ((sf >> 2) & 3) - 1; L.stiffThr = (sf >> 4) & 15; L.nonStiffThr = (sf >> 8) & 15;
+    const int evp = q[SI::EVP * c];
+    L.evmask = (unsigned)(evp & 0xff); L.evAction = (evp >> 8) & 0xff;
+#pragma unroll
+    for (int i = 0; i < M; ++i) L.EvDir[i] = ((evp >> (16 + 2 * i)) & 3) - 1;
+    L.evCount = q[SI::EVC * c];
+    return flags;
+}
+
+/* final status resolution and result store (:642-708) */
+template <class SYS, bool DENSE>
+__device__ __forceinline__ void store_results(const KArgs& p, long idx, const Lane<SYS>& L)
+{
+    constexpr int N = SYS::N;
+    const long NN = p.N;
+    int fs = L.st;
+    if (L.LAST && L.st == FLINT_SUCCESS) {}
+    else if (L.eventsOn && L.LAST && L.st == FLINT_EVENT_TERM) {}
+    else if (L.total >= p.max_steps && L.st == FLINT_SUCCESS) fs = FLINT_ERROR_MAXSTEPS;
+    else if (L.st == FLINT_ERROR_STEPSZ_TOOSMALL) {}
+    else if (L.eventsOn && L.st == FLINT_ERROR_EVENTROOT) {}
+    else if (L.st == FLINT_STIFF_PROBLEM) {}
+    else fs = FLINT_ERROR;
+    p.xf[idx] = L.X;
+#pragma unroll
+    for (int i = 0; i < N; ++i) p.yf[(long)i * NN + idx] = L.Y[i];
+    if (!p.const_step && p.stepsz) p.stepsz[idx] = L.h;
+    p.status[idx] = fs;
+    if (p.counters) {
+        p.counters[0 * NN + idx] = L.total; p.counters[1 * NN + idx] = L.acc;
+        p.counters[2 * NN + idx] = L.rej; p.counters[3 * NN + idx] = L.fcalls;
+    }
+    if (p.stifftest) p.stifftest[idx] = L.stiffOut;
+    if (p.ev_count) p.ev_count[idx] = L.evCount;
+    if (p.steps_count) p.steps_count[idx] = L.acc + 1;
+    if (DENSE && p.dense_count) p.dense_count[idx] = L.acc;
+    p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
+}
+template <class SYS>
+__device__ __forceinline__ bool keeps_going(const KArgs& p, const Lane<SYS>& L)
+{
+    return L.st == FLINT_SUCCESS && !L.LAST && L.total < p.max_steps;      /* :263 */
+}
+
+/* ===================================================================== init: one thread per trajectory (:204-259) */
+template <class METHOD, class SYS, bool FMA, bool DENSE>
+__global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ KArgs p)
+{
+    constexpr int N = SYS::N, M = SYS::M_MAX;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long NN = p.N;
+    if (idx >= NN) return;
+    SYS sys;
+    sys.load(p.sp);
+    const int m = p.m;
+    const bool const_step = p.const_step != 0;
+    Lane<SYS> L;
+    L.X = p.x0 ? p.x0[idx] : p.x0_scalar;
+    p.sd[SD<N, M>::X0 * p.scap + idx] = L.X;                              /* for the direction of integration */
+#pragma unroll
+    for (int c = 0; c < N; ++c) { L.Y[c] = p.y0[(long)c * NN + idx]; L.F0[c] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) { L.EV0[i] = 0.0; L.EvDir[i] = 0; }
+    L.Xf = p.xf[idx];
+    L.total = 0; L.acc = 0; L.rej = 0; L.fcalls = 0; L.st = FLINT_SUCCESS;
+    L.LAST = false; L.lastRej = false; L.stiffThr = 0; L.nonStiffThr = 0;
+    L.hbyhoptOld = p.szp[5];
+    L.evAction = FLINT_EVENTACTION_CONTINUE; L.evCount = 0;
+    L.hSign = sign1(L.Xf - L.X);                                            /* :94 */
+    L.h = p.stepsz ? p.stepsz[idx] : 0.0;
+    L.hmax = 0.0;
+    bool early = false;   /* argument errors: the reference returns before touching Xf/Yf (:196-199) */
+    if (const_step && (L.hSign * L.h) <= 0.0) { L.st = FLINT_ERROR_CONSTSTEPSZ; early = true; }   /* :99-103 */
+    L.stiffMode = p.stifftest ? p.stifftest[idx] : p.stiff_mode;
+    L.stiffOut = L.stiffMode;
+    if (p.stiff_present && (L.stiffMode < 0 || L.stiffMode > 2)) { L.st = FLINT_ERROR_PARAMS; early = true; }   /* :143-154 */
+    if (!p.stiff_present) L.stiffMode = 0;
+    L.evmask = p.evmask_bits;
+    L.eventsOn = p.events_on && L.evmask != 0u;                             /* :175-193 */
+    if (early) {
+        p.status[idx] = L.st;
+        if (p.counters) { p.counters[0 * NN + idx] = 0; p.counters[1 * NN + idx] = 0; p.counters[2 * NN + idx] = 0; p.counters[3 * NN + idx] = 0; }
+        p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
+        return;
+    }
+    if (L.eventsOn) {                                                       /* :216-221 */
+        double yy[N]; int da = 0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) yy[c] = L.Y[c];
+        sys.events(p.evset, L.X, yy, (1u << m) - 1u, L.EV0, L.EvDir, 0, da);
+    }
+    rhs_eval<SYS, FMA>(sys, L.Y, L.F0);                                     /* :224-225 */
+    L.fcalls = 1;
+    L.hmax = p.hmax_opt;
+    if (L.hmax == 0.0) L.hmax = fabs(L.Xf - L.X);                           /* :237 */
+    if (L.h == 0.0) {                                                       /* StepSz0Hairer, src/StepSz.f90:53-117 */
+        double t0[N], t1[N], sc0[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            sc0[c] = madd<FMA>(p.tol.rt(c), fabs(L.Y[c]), p.tol.at(c));     /* :230-234 */
+            t0[c] = L.Y[c] / sc0[c]; t1[c] = L.F0[c] / sc0[c];
+        }
+        const double d0 = norm2<FMA, N>(t0), d1 = norm2<FMA, N>(t1);
+        double h0 = (d0 <= 1.0e-5 || d1 <= 1.0e-5) ? 1.0e-6 : (0.01 * d0) / d1;
+        h0 = L.hSign * dmin(h0, L.hmax);
+        double yh[N], F1[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) yh[c] = madd<FMA>(h0, L.F0[c], L.Y[c]);
+        rhs_eval<SYS, FMA>(sys, yh, F1);
+#pragma unroll
+        for (int c = 0; c < N; ++c) t0[c] = (F1[c] - L.F0[c]) / sc0[c];
+        const double d2 = norm2<FMA, N>(t0) / h0;
+        const double dMax = dmax(d1, fabs(d2));
+        double h1;
+        if (dMax <= 1.0e-15) h1 = dmax(1.0e-6, fabs(h0) * 1.0e-3);
+        else h1 = flint_det_pow(0.01 / dMax, 1.0 / (double)METHOD::P);
+        L.h = L.hSign * dmin(dmin(100.0 * fabs(h0), h1), L.hmax);
+        L.fcalls += 1;
+    }
+    if (p.steps_on && p.steps_cap > 0) {                                    /* :254-257 */
+        p.xint[0 * NN + idx] = L.X;
+#pragma unroll
+        for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + 0) * NN + idx] = L.Y[c];
+    }
+    if (DENSE && p.dense_cap > 0) p.dxint[0 * NN + idx] = L.X;              /* :259 */
+    if (!keeps_going<SYS>(p, L)) store_results<SYS, DENSE>(p, idx, L);
+    else state_store<SYS>(p, idx, L, 0);
+}
+
+/* ===================================================================== the hot loop */
+/* EVMODE 0: no events.  1: events located inside the lane loop.  2: steps with events to locate are parked. */
+template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
 __global__ void __launch_bounds__(FLINT_BLOCK_THREADS, FLINT_MIN_BLOCKS)
-erk_integrate_kernel(const __grid_constant__ KArgs p)
+erk_step_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
+    constexpr bool EVENTS = EVMODE != 0;
     SYS sys;
     sys.load(p.sp);
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long NN = p.N;
     const int m = p.m;
     const bool const_step = p.const_step != 0;
     const double fac = const_step ? 1.0 : kLastStepExpFac;              /* :106-110 */
     const double SFl = p.szp[0], SFmin = p.szp[1], beta = p.szp[3], beta_mult = p.szp[4];
     const double expo = madd<FMA>(-beta, beta_mult, 1.0 / ((double)METHOD::Q + 1.0));   /* src/StepSz.f90:153 */
+    const long n_items = p.list_in ? (long)*p.n_in : p.N;
 
-    /* per-trajectory (loop-carried) state */
     long idx = -1;
     bool have = false, exhausted = false, first = true, pending = false;
-    double X = 0, h = 0, Xf = 0, hSign = 1, hmax = 0, hbyhoptOld = 0;
-    double Y[N], F0[N];
-    int total = 0, acc = 0, rej = 0, fcalls = 0, st = FLINT_SUCCESS;
-    bool LAST = false, lastRej = false;
-    int stiffMode = 0, stiffThr = 0, nonStiffThr = 0, stiffOut = 0;
-    double EV0[M];
-    int EvDir[M];
-    unsigned evmask = 0;
-    int evAction = FLINT_EVENTACTION_CONTINUE, evCount = 0;
-    bool eventsOn = false;
-    EvCtx<METHOD, SYS> ctx;                 /* local memory; touched only when an event has to be located */
+    Lane<SYS> L;
+    L.X = 0; L.h = 0; L.Xf = 0; L.hSign = 1; L.hmax = 0; L.hbyhoptOld = 0;
+    L.total = 0; L.acc = 0; L.rej = 0; L.fcalls = 0; L.st = FLINT_SUCCESS;
+    L.LAST = false; L.lastRej = false; L.eventsOn = false;
+    L.stiffMode = 0; L.stiffThr = 0; L.nonStiffThr = 0; L.stiffOut = 0;
+    L.evmask = 0; L.evAction = FLINT_EVENTACTION_CONTINUE; L.evCount = 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { Y[i] = 0; F0[i] = 0; }
+    for (int i = 0; i < N; ++i) { L.Y[i] = 0; L.F0[i] = 0; }
 #pragma unroll
-    for (int i = 0; i < M; ++i) { EV0[i] = 0; EvDir[i] = 0; }
-
-    /* final status resolution and result store (:642-708) */
-    auto finalize = [&]() {
-        int fs = st;
-        if (LAST && st == FLINT_SUCCESS) {}
-        else if (eventsOn && LAST && st == FLINT_EVENT_TERM) {}
-        else if (total >= p.max_steps && st == FLINT_SUCCESS) fs = FLINT_ERROR_MAXSTEPS;
-        else if (st == FLINT_ERROR_STEPSZ_TOOSMALL) {}
-        else if (eventsOn && st == FLINT_ERROR_EVENTROOT) {}
-        else if (st == FLINT_STIFF_PROBLEM) {}
-        else fs = FLINT_ERROR;
-        p.xf[idx] = X;
-#pragma unroll
-        for (int i = 0; i < N; ++i) p.yf[(long)i * NN + idx] = Y[i];
-        if (!const_step && p.stepsz) p.stepsz[idx] = h;
-        p.status[idx] = fs;
-        if (p.counters) {
-            p.counters[0 * NN + idx] = total; p.counters[1 * NN + idx] = acc;
-            p.counters[2 * NN + idx] = rej; p.counters[3 * NN + idx] = fcalls;
-        }
-        if (p.stifftest) p.stifftest[idx] = stiffOut;
-        if (p.ev_count) p.ev_count[idx] = evCount;
-        if (p.steps_count) p.steps_count[idx] = acc + 1;
-        if (DENSE && p.dense_count) p.dense_count[idx] = acc;
-        have = false;
-    };
+    for (int i = 0; i < M; ++i) { L.EV0[i] = 0; L.EvDir[i] = 0; }
+    EvCtx<METHOD, SYS> ctx;                 /* EVMODE 1 only: local memory, touched when an event has to be located */
 
     for (;;) {
-        /* ---------------- refill: take the next trajectory and initialise it (:204-259) ---------------- */
+        /* ---------------- refill: take the next trajectory from the state block ---------------- */
         if (!have && !exhausted) {
-            const long i = first ? tid : (long)atomicAdd(p.work_counter, 1ULL);
+            const long k = first ? tid : (long)atomicAdd(p.work_counter, 1ULL);
             first = false;
-            if (i < NN) {
-                idx = i;
-                have = true;
-                X = p.x0 ? p.x0[idx] : p.x0_scalar;
-#pragma unroll
-                for (int c = 0; c < N; ++c) Y[c] = p.y0[(long)c * NN + idx];
-                Xf = p.xf[idx];
-                total = 0; acc = 0; rej = 0; fcalls = 0; st = FLINT_SUCCESS;
-                LAST = false; lastRej = false; stiffThr = 0; nonStiffThr = 0;
-                hbyhoptOld = p.szp[5];
-                evAction = FLINT_EVENTACTION_CONTINUE; evCount = 0;
-                hSign = sign1(Xf - X);                                      /* :94 */
-                h = p.stepsz ? p.stepsz[idx] : 0.0;
-                bool early = false;   /* argument errors: the reference returns before touching Xf/Yf (:196-199) */
-                if (const_step && (hSign * h) <= 0.0) { st = FLINT_ERROR_CONSTSTEPSZ; early = true; }   /* :99-103 */
-                stiffMode = p.stifftest ? p.stifftest[idx] : p.stiff_mode;
-                stiffOut = stiffMode;
-                if (p.stiff_present && (stiffMode < 0 || stiffMode > 2)) { st = FLINT_ERROR_PARAMS; early = true; }   /* :143-154 */
-                if (!p.stiff_present) stiffMode = 0;
-                evmask = p.evmask_bits;
-                eventsOn = EVENTS && p.events_on && evmask != 0u;          /* :175-193 */
-                if (early) {
-                    p.status[idx] = st;
-                    if (p.counters) { p.counters[0 * NN + idx] = 0; p.counters[1 * NN + idx] = 0; p.counters[2 * NN + idx] = 0; p.counters[3 * NN + idx] = 0; }
-                    have = false;
-                } else {
-                    if (EVENTS && eventsOn) {                               /* :216-221 */
-                        double yy[N]; int da = 0;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) yy[c] = Y[c];
-                        sys.events(p.evset, X, yy, (1u << m) - 1u, EV0, EvDir, 0, da);
-                    }
-                    {                                                       /* :224-225 */
-                        rhs_eval<SYS, FMA>(sys, Y, F0);
-                    }
-                    fcalls = 1;
-                    hmax = p.hmax_opt;
-                    if (hmax == 0.0) hmax = fabs(Xf - X);                   /* :237 */
-                    if (h == 0.0) {                                         /* StepSz0Hairer, src/StepSz.f90:53-117 */
-                        double t0[N], t1[N], sc0[N];
-#pragma unroll
-                        for (int c = 0; c < N; ++c) {
-                            sc0[c] = madd<FMA>(p.tol.rt(c), fabs(Y[c]), p.tol.at(c));   /* :230-234 */
-                            t0[c] = Y[c] / sc0[c]; t1[c] = F0[c] / sc0[c];
-                        }
-                        const double d0 = norm2<FMA, N>(t0), d1 = norm2<FMA, N>(t1);
-                        double h0 = (d0 <= 1.0e-5 || d1 <= 1.0e-5) ? 1.0e-6 : (0.01 * d0) / d1;
-                        h0 = hSign * dmin(h0, hmax);
-                        double yh[N], F1[N];
-#pragma unroll
-                        for (int c = 0; c < N; ++c) yh[c] = madd<FMA>(h0, F0[c], Y[c]);
-                        rhs_eval<SYS, FMA>(sys, yh, F1);
-#pragma unroll
-                        for (int c = 0; c < N; ++c) t0[c] = (F1[c] - F0[c]) / sc0[c];
-                        const double d2 = norm2<FMA, N>(t0) / h0;
-                        const double dMax = dmax(d1, fabs(d2));
-                        double h1;
-                        if (dMax <= 1.0e-15) h1 = dmax(1.0e-6, fabs(h0) * 1.0e-3);
-                        else h1 = flint_det_pow(0.01 / dMax, 1.0 / (double)METHOD::P);
-                        h = hSign * dmin(dmin(100.0 * fabs(h0), h1), hmax);
-                        fcalls += 1;
-                    }
-                    if (p.steps_on && p.steps_cap > 0) {                    /* :254-257 */
-                        p.xint[0 * NN + idx] = X;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + 0) * NN + idx] = Y[c];
-                    }
-                    if (DENSE && p.dense_cap > 0) p.dxint[0 * NN + idx] = X;   /* :259 */
-                    if (!(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
+            if (k < n_items) {
+                const long i = p.list_in ? (long)p.list_in[k] : k;
+                if (i >= 0) {
+                    const int flags = state_load<SYS>(p, i, L);
+                    if (!(flags & kFlagDone)) { idx = i; have = true; }
                 }
             } else exhausted = true;
         }
         if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
-        /* ---------------- deferred: finish an accepted step whose events have to be located ---------------- */
-        if (EVENTS && pending) {
-            deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, hSign);
-            X = ctx.X; h = ctx.h; hbyhoptOld = ctx.hbyhoptOld; lastRej = ctx.lastRej; LAST = ctx.LAST; st = ctx.st;
-            fcalls = ctx.fcalls; evmask = ctx.evmask; evAction = ctx.action; evCount = ctx.evcount;
+        /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
+        if (EVMODE == 1 && pending) {
+            deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, L.hSign);
+            L.X = ctx.X; L.h = ctx.h; L.hbyhoptOld = ctx.hbyhoptOld; L.lastRej = ctx.lastRej; L.LAST = ctx.LAST; L.st = ctx.st;
+            L.fcalls = ctx.fcalls; L.evmask = ctx.evmask; L.evAction = ctx.action; L.evCount = ctx.evcount;
 #pragma unroll
-            for (int i = 0; i < N; ++i) { Y[i] = ctx.Y[i]; F0[i] = ctx.F0old[i]; }
+            for (int i = 0; i < N; ++i) { L.Y[i] = ctx.Y[i]; L.F0[i] = ctx.F0old[i]; }
 #pragma unroll
-            for (int i = 0; i < M; ++i) { EV0[i] = ctx.EV0[i]; EvDir[i] = ctx.EvDir[i]; }
+            for (int i = 0; i < M; ++i) { L.EV0[i] = ctx.EV0[i]; L.EvDir[i] = ctx.EvDir[i]; }
             pending = false;
-            if (!(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
+            if (!keeps_going<SYS>(p, L)) { store_results<SYS, DENSE>(p, idx, L); have = false; }
         }
 
         /* ---------------- one step attempt for every lane that owns a trajectory (:263-637) ---------------- */
         if (have) {
-            if (hSign * (madd<FMA>(fac, h, X) - Xf) > 0.0) { h = Xf - X; LAST = true; }   /* :268-271 */
+            if (L.hSign * (madd<FMA>(fac, L.h, L.X) - L.Xf) > 0.0) { L.h = L.Xf - L.X; L.LAST = true; }   /* :268-271 */
+            const double h = L.h;
             double ks[METHOD::NSLOT][N], Ynew[N], Ypre[N], Err;
-            METHOD::template step<SYS, FMA, DENSE>(sys, X, Y, F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
-            total += 1;
+            METHOD::template step<SYS, FMA, DENSE>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
+            L.total += 1;
             double hbyhopt = 1.0;
             if (!const_step) hbyhopt = flint_det_pow(Err, expo);            /* src/StepSz.f90:153 */
+            bool parked = false;
             if (Err <= 1.0) {                                               /* :283 */
-                fcalls += METHOD::FC_ACC;
-                acc += 1;
-                if (p.step_once) LAST = true;                               /* :289 */
+                L.fcalls += METHOD::FC_ACC;
+                L.acc += 1;
+                if (p.step_once) L.LAST = true;                             /* :289 */
                 bool bip_counted = false;                                   /* BipComputed :292 */
 
-                if (stiffMode == 1 || stiffMode == 2) {                     /* CheckStiffness :299-308, :767-798 */
+                if (L.stiffMode == 1 || L.stiffMode == 2) {                 /* CheckStiffness :299-308, :767-798 */
                     bool stiff = false;
-                    if ((acc % kStiffTestSteps) == 0 || stiffThr > 0) {
+                    if ((L.acc % kStiffTestSteps) == 0 || L.stiffThr > 0) {
                         double dk[N], dy[N];
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
@@ -523,88 +647,160 @@ erk_integrate_kernel(const __grid_constant__ KArgs p)
                         const double sN = norm2<FMA, N>(dk), sD = norm2<FMA, N>(dy);
                         double hLamb = 0.0;
                         if (sD > 0.0) hLamb = (fabs(h) * sN) / sD;
-                        if (hLamb > 6.1) { nonStiffThr = 0; stiffThr += 1; if (stiffThr == 15) stiff = true; }
-                        else { nonStiffThr += 1; if (nonStiffThr == 6) stiffThr = 0; }
+                        if (hLamb > 6.1) { L.nonStiffThr = 0; L.stiffThr += 1; if (L.stiffThr == 15) stiff = true; }
+                        else { L.nonStiffThr += 1; if (L.nonStiffThr == 6) L.stiffThr = 0; }
                     }
                     if (stiff) {
-                        stiffOut = -1;
-                        if (stiffMode == 1) { st = FLINT_STIFF_PROBLEM; LAST = true; }
+                        L.stiffOut = -1;
+                        if (L.stiffMode == 1) { L.st = FLINT_STIFF_PROBLEM; L.LAST = true; }
                     }
                 }
 
                 bool rare = false;
-                if (EVENTS && eventsOn) {                                   /* :313-552 */
+                if (EVENTS && L.eventsOn) {                                 /* :313-552 */
                     double EV1[M], yy[N];
 #pragma unroll
                     for (int i = 0; i < M; ++i) EV1[i] = 0.0;
 #pragma unroll
                     for (int c = 0; c < N; ++c) yy[c] = Ynew[c];
                     int da = 0;
-                    sys.events(p.evset, X + h, yy, (1u << m) - 1u, EV1, EvDir, 0, da);   /* :324-325 */
+                    sys.events(p.evset, L.X + h, yy, (1u << m) - 1u, EV1, L.EvDir, 0, da);   /* :324-325 */
                     unsigned det = 0, ss = 0;
 #pragma unroll
                     for (int i = 0; i < M; ++i) {
                         if (i < m) {
-                            if (detect_event((evmask >> i) & 1u, EvDir[i], EV0[i], EV1[i])) det |= (1u << i);   /* :326-328 */
-                            if (!(p.ev_stepsz[i] == 0.0 || p.ev_stepsz[i] > hSign * h)) ss |= (1u << i);        /* :332-335 */
+                            if (detect_event((L.evmask >> i) & 1u, L.EvDir[i], L.EV0[i], EV1[i])) det |= (1u << i);   /* :326-328 */
+                            if (!(p.ev_stepsz[i] == 0.0 || p.ev_stepsz[i] > L.hSign * h)) ss |= (1u << i);            /* :332-335 */
                         }
                     }
-                    if (ss && !bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }   /* :337-344, quirk Q1 (lazy) */
-                    rare = det || (ss & evmask);
-                    if (rare) {            /* stash the step; it is committed at the top of the next lane iteration */
-                        ctx.X = X; ctx.h = h; ctx.h_stage = h;
+                    if (ss && !bip_counted) { L.fcalls += METHOD::FC_DENSE; bip_counted = true; }   /* :337-344, quirk Q1 (lazy) */
+                    rare = det || (ss & L.evmask);
+                    if (rare) {
+                        if (EVMODE == 1) {     /* stash the step; it is committed at the top of the next lane iteration */
+                            ctx.X = L.X; ctx.h = h; ctx.h_stage = h;
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            ctx.Y[i] = Y[i]; ctx.Y1[i] = Ynew[i]; ctx.F0old[i] = F0[i]; ctx.ENY[i] = yy[i];
-                            ctx.F0new[i] = ks[METHOD::SLOT_F0NEW][i];
+                            for (int i = 0; i < N; ++i) {
+                                ctx.Y[i] = L.Y[i]; ctx.Y1[i] = Ynew[i]; ctx.F0old[i] = L.F0[i]; ctx.ENY[i] = yy[i];
+                                ctx.F0new[i] = ks[METHOD::SLOT_F0NEW][i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < M; ++i) { ctx.EV0[i] = L.EV0[i]; ctx.EV1[i] = EV1[i]; ctx.EvDir[i] = L.EvDir[i]; }
+                            ctx.evmask = L.evmask; ctx.det = det; ctx.ss = ss; ctx.action = L.evAction; ctx.st = L.st; ctx.fcalls = L.fcalls;
+                            ctx.evcount = L.evCount; ctx.LAST = L.LAST; ctx.bip_counted = bip_counted; ctx.haveB = false;
+                            ctx.Err = Err; ctx.hbyhopt = hbyhopt; ctx.hbyhoptOld = L.hbyhoptOld; ctx.hmax = L.hmax; ctx.acc = L.acc;
+                            ctx.lastRej = L.lastRej;
+                            pending = true;
+                        } else {               /* EVMODE 2: park the trajectory with the data of this step */
+                            using D = SD<N, M>;
+                            const long c = p.scap;
+                            state_store<SYS>(p, idx, L, bip_counted ? kFlagBipCounted : 0);
+                            double* d = p.sd + idx;
+                            d[D::HSTEP * c] = h; d[D::ERR * c] = Err; d[D::HBH * c] = hbyhopt;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { d[(D::Y1 + i) * c] = Ynew[i]; d[(D::F0N + i) * c] = ks[METHOD::SLOT_F0NEW][i]; }
+#pragma unroll
+                            for (int i = 0; i < M; ++i) d[(D::EV1 + i) * c] = EV1[i];
+                            p.si[SI::DET * c + idx] = (int)det; p.si[SI::SS * c + idx] = (int)ss;
+                            p.list_out[atomicAdd(p.n_out, 1ULL)] = (int)idx;
+                            parked = true; have = false;
                         }
-#pragma unroll
-                        for (int i = 0; i < M; ++i) { ctx.EV0[i] = EV0[i]; ctx.EV1[i] = EV1[i]; ctx.EvDir[i] = EvDir[i]; }
-                        ctx.evmask = evmask; ctx.det = det; ctx.ss = ss; ctx.action = evAction; ctx.st = st; ctx.fcalls = fcalls;
-                        ctx.evcount = evCount; ctx.LAST = LAST; ctx.bip_counted = bip_counted; ctx.haveB = false;
-                        ctx.Err = Err; ctx.hbyhopt = hbyhopt; ctx.hbyhoptOld = hbyhoptOld; ctx.hmax = hmax; ctx.acc = acc; ctx.lastRej = lastRej;
-                        pending = true;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < M; ++i) EV0[i] = EV1[i];        /* :550 */
+                        for (int i = 0; i < M; ++i) L.EV0[i] = EV1[i];      /* :550 */
                     }
                 }
                 if (!rare) {
                     double B[PS + 1][N];       /* dead unless DENSE */
-                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Ynew, B, p.coef);
+                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, L.Y, h, Ynew, B, p.coef);
                     double hio = h;
-                    commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, eventsOn, evAction, hSign, hmax, X, Y, F0, hio, hbyhoptOld, lastRej, LAST, st,
-                                                                 fcalls, acc, h, Ynew, ks[METHOD::SLOT_F0NEW], Err, hbyhopt, bip_counted, Ynew, B);
-                    h = hio;
+                    commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
+                                                                 L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, ks[METHOD::SLOT_F0NEW], Err, hbyhopt,
+                                                                 bip_counted, Ynew, B);
+                    L.h = hio;
                 }
             } else {                                                        /* :607-624 */
-                fcalls += METHOD::FC_REJ;
-                if (acc >= 1) rej += 1;
-                h = h * dmax(SFmin, SFl / hbyhopt);                         /* src/StepSz.f90:176, :627 */
-                lastRej = true;
-                LAST = false;
-                if (!const_step && fabs(h) * 0.01 <= fabs(X) * kEps) st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
+                L.fcalls += METHOD::FC_REJ;
+                if (L.acc >= 1) L.rej += 1;
+                L.h = h * dmax(SFmin, SFl / hbyhopt);                       /* src/StepSz.f90:176, :627 */
+                L.lastRej = true;
+                L.LAST = false;
+                if (!const_step && fabs(L.h) * 0.01 <= fabs(L.X) * kEps) L.st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
             }
-            if (!pending && !(st == FLINT_SUCCESS && !LAST && total < p.max_steps)) finalize();
+            if (!pending && !parked && !keeps_going<SYS>(p, L)) { store_results<SYS, DENSE>(p, idx, L); have = false; }
         }
     }
 }
 
-/* Host-side launcher signature shared by all instantiations (inst_*.cu). */
-
-template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
-cudaError_t launch_erk(const KArgs& a, int grid, int block, cudaStream_t s)
+/* ===================================================================== parked trajectories: locate + commit */
+template <class METHOD, class SYS, bool FMA, bool DENSE>
+__global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ KArgs p)
 {
-    KArgs b = a;
-    METHOD::load_coefficients(b.coef);
-    erk_integrate_kernel<METHOD, SYS, FMA, EVENTS, DENSE><<<grid, block, 0, s>>>(b);
+    constexpr int N = SYS::N, M = SYS::M_MAX;
+    using D = SD<N, M>;
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long n_parked = (long)*p.n_in;
+    if (j == 0) {                                   /* stream-ordered between two step passes: recycle their counters */
+        *p.work_counter = p.counter_reset;
+        *p.n_out = 0ULL;
+    }
+    if (j >= n_parked) return;
+    const long idx = p.list_in[j];
+    SYS sys;
+    sys.load(p.sp);
+    Lane<SYS> L;
+    const int flags = state_load<SYS>(p, idx, L);
+    const long c = p.scap;
+    const double* d = p.sd + idx;
+    EvCtx<METHOD, SYS> ctx;
+    ctx.X = L.X; ctx.h = d[D::HSTEP * c]; ctx.h_stage = ctx.h;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ctx.Y[i] = L.Y[i]; ctx.Y1[i] = d[(D::Y1 + i) * c]; ctx.F0old[i] = L.F0[i]; ctx.ENY[i] = ctx.Y1[i];
+        ctx.F0new[i] = d[(D::F0N + i) * c];
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) { ctx.EV0[i] = L.EV0[i]; ctx.EV1[i] = d[(D::EV1 + i) * c]; ctx.EvDir[i] = L.EvDir[i]; }
+    ctx.evmask = L.evmask; ctx.det = (unsigned)p.si[SI::DET * c + idx]; ctx.ss = (unsigned)p.si[SI::SS * c + idx];
+    ctx.action = L.evAction; ctx.st = L.st; ctx.fcalls = L.fcalls;
+    ctx.evcount = L.evCount; ctx.LAST = L.LAST; ctx.bip_counted = (flags & kFlagBipCounted) != 0; ctx.haveB = false;
+    ctx.Err = d[D::ERR * c]; ctx.hbyhopt = d[D::HBH * c]; ctx.hbyhoptOld = L.hbyhoptOld; ctx.hmax = L.hmax; ctx.acc = L.acc;
+    ctx.lastRej = L.lastRej;
+    deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, L.hSign);
+    L.X = ctx.X; L.h = ctx.h; L.hbyhoptOld = ctx.hbyhoptOld; L.lastRej = ctx.lastRej; L.LAST = ctx.LAST; L.st = ctx.st;
+    L.fcalls = ctx.fcalls; L.evmask = ctx.evmask; L.evAction = ctx.action; L.evCount = ctx.evcount;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { L.Y[i] = ctx.Y[i]; L.F0[i] = ctx.F0old[i]; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) { L.EV0[i] = ctx.EV0[i]; L.EvDir[i] = ctx.EvDir[i]; }
+    if (!keeps_going<SYS>(p, L)) store_results<SYS, DENSE>(p, idx, L);     /* the next pass skips it (done flag) */
+    else state_store<SYS>(p, idx, L, 0);
+}
+
+/* Host-side launchers shared by all instantiations (inst_*.cu). */
+template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
+cudaError_t launch_step(const KArgs& a, int grid, int block, cudaStream_t s)
+{
+    erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE><<<grid, block, 0, s>>>(a);
     return cudaGetLastError();
 }
-template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
-cudaError_t occupancy_erk(int* blocks_per_sm, int block)
+template <class METHOD, class SYS, bool FMA, bool DENSE>
+cudaError_t launch_init(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_integrate_kernel<METHOD, SYS, FMA, EVENTS, DENSE>, block, 0);
+    erk_init_kernel<METHOD, SYS, FMA, DENSE><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
 }
+template <class METHOD, class SYS, bool FMA, bool DENSE>
+cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
+{
+    erk_event_kernel<METHOD, SYS, FMA, DENSE><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
+cudaError_t occupancy_step(int* blocks_per_sm, int block)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, block, 0);
+}
+template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }
 
 }  // namespace flint
 #endif

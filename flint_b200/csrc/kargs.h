@@ -56,6 +56,11 @@ struct KArgs {
     long ev_cap; int* ev_count; double* ev_rec;          /* [(n+2)][cap][N] */
     int steps_on; long steps_cap; double* xint; double* yint; int* steps_count;   /* IntStepsOn output */
     long dense_cap; double* dxint; double* dbip; int* dense_count; int nI; int istates[FLINT_MAX_N];   /* InterpOn storage */
+    /* trajectory state block + work lists (erk_kernel.cuh) */
+    double* sd; int* si; long scap;              /* [fields][scap] */
+    const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */
+    int* list_out; unsigned long long* n_out;    /* EVMODE 2: trajectories parked by this pass */
+    unsigned long long counter_reset;            /* erk_event_kernel re-arms work_counter with this */
     unsigned long long* work_counter;
     double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by launch_erk) */
 };
@@ -78,8 +83,13 @@ typedef cudaError_t (*occupancy_fn)(int* blocks_per_sm, int block);
 struct KernelEntry {
     int method, system;
     bool fma, events, dense;
-    launch_fn launch;
-    occupancy_fn occupancy;
+    launch_fn init;              /* erk_init_kernel */
+    launch_fn step;              /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
+    launch_fn step_park;         /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
+    launch_fn event;             /* erk_event_kernel (NULL when events == false) */
+    occupancy_fn occupancy, occupancy_park;
+    void (*load_coefficients)(double* dst);
+    int n_state_doubles, n_state_ints;
 };
 void register_kernel(const KernelEntry&);
 const KernelEntry* find_kernel(int method, int system, bool fma, bool events, bool dense);

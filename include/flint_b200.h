@@ -140,6 +140,9 @@ typedef struct {
     long dense_cap;     /* dense-output steps stored per trajectory when InterpOn (0 = MaxSteps, as the reference) */
     int block_threads;  /* 0 = library default */
     int blocks_per_sm;  /* 0 = library default */
+    int event_mode;     /* how accepted steps with an event to locate are handled: 0 = automatic, 1 = inside the
+                           stepping kernel, 2 = parked and located in batches by a separate kernel (the default
+                           choice unless an unmasked event has an EventStepSz).  Results are identical. */
 } flint_exec;
 
 /* ---- DiffEqSys ---- */

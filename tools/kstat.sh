@@ -1,9 +1,16 @@
 #!/bin/bash
 # kstat.sh <inst-name> [extra nvcc flags]: compile one instantiation file, print registers/spills of
-# the bench variants and dump SASS to /tmp/<inst-name>.sass  (development aid)
-set -e
+# its kernels and dump SASS to /tmp/<inst-name>.sass  (development aid)
 name=$1; shift
 cd /root/repo/flint_b200/csrc
-nvcc -std=c++17 -O3 --fmad=false -lineinfo -gencode arch=compute_100a,code=sm_100a -Xptxas -v -I . "$@" -c inst/inst_$name.cu -o /tmp/$name.o 2>&1 \
-  | grep -A2 "Compiling entry function" | grep -E "Compiling|registers|spill" | sed -e 's/ptxas info    ://' -e "s/Compiling entry function '_ZN5flint20erk_integrate_kernelINS_//" -e "s/EEEvNS_5KArgsE' for 'sm_100a'//" | paste - - - | cut -c1-220
+nvcc -std=c++17 -O3 --fmad=false -lineinfo -gencode arch=compute_100a,code=sm_100a -Xptxas -v -I . "$@" -c inst/inst_$name.cu -o /tmp/$name.o > /tmp/$name.log 2>&1
+python3 - /tmp/$name.log <<'PY'
+import re,sys
+t=open(sys.argv[1]).read()
+for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", t):
+    n=m.group(1)
+    n=re.sub(r'_ZN5flint','',n); n=re.sub(r'INS_\d+Method','<',n); n=re.sub(r'ENS_\d+Sys',',',n); n=n.replace('EEEvNS_5KArgsE','>')
+    n=re.sub(r'ELb([01])',r',\1',n); n=re.sub(r'ELi(\d)',r',m\1',n)
+    print("%-60s stack %5s spillst %5s spillld %5s regs %s"%(n,m.group(2),m.group(3),m.group(4),m.group(5)))
+PY
 cuobjdump -sass /tmp/$name.o > /tmp/$name.sass

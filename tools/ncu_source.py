@@ -44,3 +44,10 @@ if '--dump' in sys.argv:
     i = sys.argv.index('--dump'); lo, hi = int(sys.argv[i + 1], 16), int(sys.argv[i + 2], 16)
     for a, t, ex, sm, r in recs:
         if lo <= a < hi: print('%6x %-64s %6dM %6d' % (a, t[:64], ex // 1000000, sm))
+if '--div' in sys.argv:
+    ith = hdr.index("Thread Instructions Executed")
+    lowi = lows = 0
+    for a, t, ex, sm, r in recs:
+        th = int(r[ith])
+        if ex and th / ex < 8: lowi += ex; lows += sm
+    print("instructions executed with < 8 active lanes: %.1f%% of warp instructions, %.1f%% of samples" % (100 * lowi / tot, 100 * lows / stot))
