@@ -300,6 +300,9 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     KArgs a{};
     a.N = N; a.n = n; a.m = m; a.evset = sys.eventset_id;
     for (int i = 0; i < 8; ++i) a.sp[i] = sys.sp[i];
+    /* derived parameter, computed once here with the same IEEE operation the reference's F performs on every call
+     * (`1.0_WP - mu`, tests/test_CR3BP.f90:178): the kernels read it from the parameter block */
+    if (sys.system_id == FLINT_SYS_CR3BP_PLANAR || sys.system_id == FLINT_SYS_CR3BP_SPATIAL) a.sp[7] = 1.0 - a.sp[0];
     a.max_steps = me->max_steps;
     for (int i = 0; i < FLINT_MAX_N; ++i) { a.tol.a[i] = me->atol[i]; a.tol.r[i] = me->rtol[i]; }
     a.tol.scalar = me->scalar_tol ? 1 : 0;

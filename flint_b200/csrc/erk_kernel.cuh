@@ -184,22 +184,27 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
         for (int ev = 0; ev < m; ++ev) {
             if (!((c.evmask >> ev) & 1u) || !((c.ss >> ev) & 1u)) continue;
             ensure_bip<METHOD, SYS, FMA>(sys, p, c);
-            double V0[M], V1[M];
-            for (int i = 0; i < M; ++i) { V0[i] = EV0[i][0]; V1[i] = EV1[i][0]; }
+            /* only event `ev` is evaluated inside the step (EvalEvents(ev) = 1), so its two bracket values are scalars */
+            double v0 = EV0[ev][0], v1 = EV1[ev][0];
             const double Eventh = hSign * p.ev_stepsz[ev];
             EventX1 = X + Eventh;
-            const double Vh = EV1[ev][0];
+            const double Vh = v1;
             c.det &= ~(1u << ev);
             bool last = false;
             while (EventX1 <= (X + c.h)) {                               /* :372 (quirk Q7) */
                 if (EventX1 != (X + c.h)) {
+                    double Vt[M];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) Vt[i] = 0.0;
                     interp_y<FMA, PS, N>(EventX1, X, c.h, c.B, c.ENY);
-                    sys.events(p.evset, EventX1, c.ENY, 1u << ev, V1, c.EvDir, 0, dummy_action);
-                } else V1[ev] = Vh;
-                if (detect_event((c.evmask >> ev) & 1u, c.EvDir[ev], V0[ev], V1[ev])) {
+                    sys.events(p.evset, EventX1, c.ENY, 1u << ev, Vt, c.EvDir, 0, dummy_action);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) if (i == ev) v1 = Vt[i];
+                } else v1 = Vh;
+                if (detect_event((c.evmask >> ev) & 1u, c.EvDir[ev], v0, v1)) {
                     c.det |= (1u << ev);
                     const int slot = nSS[ev] - 1;
-                    EX0[ev][slot] = EventX0; EX1[ev][slot] = EventX1; EV0[ev][slot] = V0[ev]; EV1[ev][slot] = V1[ev];
+                    EX0[ev][slot] = EventX0; EX1[ev][slot] = EventX1; EV0[ev][slot] = v0; EV1[ev][slot] = v1;
                     nSS[ev] = nSS[ev] + 1;
                     if (nSS[ev] > kMaxSS) break;
                 }
@@ -207,7 +212,7 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
                 EventX0 = EventX1;
                 EventX1 = EventX1 + Eventh;
                 if (EventX1 > X + c.h) { EventX1 = X + c.h; last = true; }
-                V0[ev] = V1[ev];
+                v0 = v1;
             }
             if (nSS[ev] > 1) nSS[ev] = nSS[ev] - 1;
         }
@@ -604,7 +609,14 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 }
             } else exhausted = true;
         }
+#if FLINT_SYNC_BLOCK
+        /* one barrier per step attempt keeps the warps of a CTA in the same part of the loop, so they
+         * share instruction-cache fills instead of evicting each other's lines (the hot loop is about the
+         * size of the 32 KB L1.5 instruction cache) */
+        if (__syncthreads_and(!have && exhausted)) break;
+#else
         if (__all_sync(0xffffffffu, !have && exhausted)) break;
+#endif
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
         if (EVMODE == 1 && pending) {

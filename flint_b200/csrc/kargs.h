@@ -11,6 +11,9 @@
 #ifndef FLINT_MIN_BLOCKS
 #define FLINT_MIN_BLOCKS 4
 #endif
+#ifndef FLINT_SYNC_BLOCK
+#define FLINT_SYNC_BLOCK 1
+#endif
 #define FLINT_DEFAULT_BLOCK FLINT_BLOCK_THREADS
 #define FLINT_MAX_BLOCK FLINT_BLOCK_THREADS
 

@@ -67,8 +67,8 @@ struct SysCR3BPPlanar {
     static constexpr int N = 6;
     static constexpr int M_MAX = 3;
     static constexpr int ID = FLINT_SYS_CR3BP_PLANAR;
-    double mu, omm;   /* omm = 1 - mu (one rounding, as `1.0_WP-mu` at run time) */
-    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = 1.0 - mu; }
+    double mu, omm;   /* omm = 1 - mu (one rounding, as `1.0_WP-mu` at run time; formed on the host, capi.cu) */
+    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
     static constexpr int NIN = 4, NOUT = 2;
     __host__ __device__ static constexpr int in_idx(int i) { return i < 2 ? i : i + 1; }          /* y0 y1 y3 y4 */
@@ -136,7 +136,7 @@ struct SysCR3BPSpatial {
     static constexpr int M_MAX = 1;
     static constexpr int ID = FLINT_SYS_CR3BP_SPATIAL;
     double mu, omm;
-    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = 1.0 - mu; }
+    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
     static constexpr int NIN = 5, NOUT = 3;
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y4 */

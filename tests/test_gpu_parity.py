@@ -77,6 +77,37 @@ def test_unmasked_substep_scanning_and_changesoly(arith):
     assert (g["nEvents"] >= 2).all()
 
 
+@pytest.mark.parametrize("event_mode", [1, 2])
+def test_event_modes_are_equivalent(event_mode):
+    """Events located inside the stepping kernel (1) and parked + located in batches (2) both equal the
+    oracle: README two-event set, TERMINATE, RESTARTINT, unmasked sub-step scanning with CHANGESOLY (in
+    mode 2 that parks on nearly every step: many rounds, then the in-loop mop-up pass), the two-body
+    apsis event (CONTINUE without MASK: an event per half period) and events + dense output."""
+    for eventset in (F.FLINT_EVSET_XY_CROSSING, F.FLINT_EVSET_CR3BP_SAMPLE3_TERM, F.FLINT_EVSET_CR3BP_SAMPLE3_RESTART):
+        case = K.cr3bp_case(F.ERK_DOP853, 1e-11, 0, eventset=eventset)
+        y0 = P.cr3bp_ensemble(200, start=7000)
+        K.compare_batch(case.run_gpu(y0, event_mode=event_mode), case.run_oracle(y0), case, "mode %d evset %d" % (event_mode, eventset))
+    case = K.cr3bp_case(F.ERK_DOP54, 1e-9, 1, norb=0.3, event_mask=[1, 1, 1], event_stepsz=[1e-4, 0.0, 0.0],
+                        event_options=[F.FLINT_EVENTOPTION_STEPBEGIN, F.FLINT_EVENTOPTION_ROOTFINDING, F.FLINT_EVENTOPTION_STEPEND],
+                        max_events=8)
+    y0 = P.cr3bp_ensemble(64, start=9100)
+    K.compare_batch(case.run_gpu(y0, event_mode=event_mode), case.run_oracle(y0), case, "mode %d scan" % event_mode)
+    case = K.twobody_case(F.ERK_VERNER65E, 1e-10, 0, nper=6, eventset=F.FLINT_EVSET_APSIS, max_events=16)
+    y0 = P.perturbed_ensemble(P.TBP_Y0, 128)
+    g = case.run_gpu(y0, event_mode=event_mode)
+    K.compare_batch(g, case.run_oracle(y0), case, "mode %d apsis" % event_mode)
+    assert (g["nEvents"] >= 11).all()
+    case = K.cr3bp_case(F.ERK_VERNER98R, 1e-10, 1, norb=1.0, interp_on=True, eventset=F.FLINT_EVSET_XY_CROSSING)
+    y0 = P.cr3bp_ensemble(64, start=444)
+    xarr = np.linspace(0.0, case.xf, 33)
+    xarr[-1] = case.xf
+    g, o = case.run_gpu(y0, event_mode=event_mode), case.run_oracle(y0, xarr=xarr)
+    K.compare_batch(g, o, case, "mode %d dense" % event_mode)
+    st, yarr, ist = g["erk"].InterpolateBatch(xarr, 64)
+    assert st == 0 and (ist == 0).all()
+    K.assert_bit_equal(yarr, o["yarr"], "Yarr mode %d" % event_mode)
+
+
 @pytest.mark.parametrize("arith", [0, 1])
 @pytest.mark.parametrize("method", METHODS)
 def test_lorenz_no_events(method, arith):

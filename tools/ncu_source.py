@@ -51,3 +51,12 @@ if '--div' in sys.argv:
         th = int(r[ith])
         if ex and th / ex < 8: lowi += ex; lows += sm
     print("instructions executed with < 8 active lanes: %.1f%% of warp instructions, %.1f%% of samples" % (100 * lowi / tot, 100 * lows / stot))
+if '--hot' in sys.argv:
+    mx = sorted(ex for a, t, ex, sm, r in recs)[-200]       # a typical per-attempt count
+    hot = [(a, t, ex, sm) for a, t, ex, sm, r in recs if ex >= 0.25 * mx]
+    print("per-attempt count ~%d; hot instructions (>= 25%% of it): %d = %.1f KB; 128B lines touched: %d = %.1f KB" % (
+        mx, len(hot), len(hot) * 16 / 1024, len({a // 128 for a, _, _, _ in hot}), len({a // 128 for a, _, _, _ in hot}) / 8))
+    hh = collections.Counter(opname(t) for a, t, ex, sm in hot)
+    print("  hot static mix:", ", ".join("%s %d" % kv for kv in hh.most_common(16)))
+    b = collections.Counter(a // 1024 for a, _, _, _ in hot)
+    print("  hot KB map:", " ".join("%x:%d" % (k * 1024, v) for k, v in sorted(b.items())))
