@@ -255,7 +255,7 @@ def main_ours(a, rank, world, local_rank):
                    "arith": a.arith, "l2": "256 MB flush between timed iterations", "timing": "CUDA events on the launch stream, max over ranks",
                    "success_fraction": float(agg[1]) / total_orbits, "host_and_device_results_identical": same},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": traffic, "kernel": "erk_integrate_kernel<DOP853,CR3BPPlanar,%s,events>" % a.arith,
+                     "traffic": traffic, "kernel": "erk_step_kernel<DOP853,CR3BPPlanar,%s,park,no-dense> (2 passes; + erk_init_kernel, erk_event_kernel < 1 %% of the step)" % a.arith,
                      "peak_source": "DFMA microbenchmark measured in this run (flint_b200_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                      "algorithmic_flop_per_orbit": flops_step / n},
         "e2e": {"value": e2e_value, "unit": "orbits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

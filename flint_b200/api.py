@@ -72,7 +72,7 @@ class _EventsOut(C.Structure):
 
 class _Exec(C.Structure):
     _fields_ = [("mem", C.c_int), ("device", C.c_int), ("stream", C.c_void_p), ("async_", C.c_int),
-                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int)]
+                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int)]
 
 
 LIB_PATH = os.environ.get("FLINT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflint_b200.so")
@@ -307,7 +307,7 @@ class ERK:
     def IntegrateBatch(self, X0, Y0, Xf, StepSz=None, UseConstStepSz=None, StepAdvance=None, IntStepsOn=None,
                        EventMask=None, EventStates=False, StiffTest=None, params=None, MaxEvents=4, StepsCap=None,
                        out=None, device=0, stream=None, dense_cap=0, block_threads=0, blocks_per_sm=0, want_counters=True,
-                       event_mode=0):
+                       event_mode=0, plane_variant=0):
         """Y0: (n, N) structure-of-arrays, numpy (host buffers: the call stages H2D/D2H itself) or a
         torch CUDA tensor (device buffers: nothing is copied).  Xf scalar or (N,).  Returns a dict of
         SoA outputs (numpy or torch, matching the input kind)."""
@@ -367,7 +367,7 @@ class ERK:
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
         ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, int(dense_cap), int(block_threads),
-                   int(blocks_per_sm), int(event_mode))
+                   int(blocks_per_sm), int(event_mode), int(plane_variant))
         x0s = float(X0) if x0v is None else 0.0
         st = lib().flint_erk_integrate_batch(self._h, N, x0s, _ptr(x0v), _ptr(Y0), _ptr(xf), _ptr(yf), _ptr(h), C.byref(io),
                                              _ptr(counters), _ptr(status), C.byref(steps) if steps else None,
@@ -404,7 +404,7 @@ class ERK:
             Xarr = np.ascontiguousarray(np.asarray(Xarr, dtype=np.float64))
             yarr = out if out is not None else np.empty(shape)
             status = np.zeros((N,), dtype=np.int32)
-        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, 0, 0, 0, 0)
+        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, 0, 0, 0, 0, 0)
         st = lib().flint_erk_interpolate_batch(self._h, _ptr(Xarr), G, _ptr(yarr), int(layout), _ptr(status),
                                                int(SaveInterpCoeffs is not None), int(bool(SaveInterpCoeffs)), C.byref(ex))
         self.status = st

@@ -248,7 +248,7 @@ struct DevBuf {                        /* RAII device scratch for FLINT_MEM_HOST
 
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
-    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0;
 };
 
 }  // namespace
@@ -414,9 +414,18 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     const long need = (N + block - 1) / block;
     if (grid > need) grid = need;
     const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
-    const unsigned long long ctr0[3] = {first_free, 0ULL, 0ULL};
+    /* plane variant: trajectories with identically zero components (csrc/systems.cuh: SysCR3BPPlanarZ).  The dropped
+     * components contribute (0/Sc)^2 to the error norms, so Sc = ATol must be positive there. */
+    bool try_plane = ke->step_plane != nullptr && (!events_on || park) && ex.plane_variant != 2;
+    if (try_plane) {
+        unsigned zp = sys.system_id == FLINT_SYS_CR3BP_PLANAR ? ((1u << 2) | (1u << 5)) : 0u;
+        for (int c = 0; c < n; ++c)
+            if (((zp >> c) & 1u) && !(me->atol[me->scalar_tol ? 0 : c] > 0.0)) try_plane = false;
+    }
+    const unsigned long long ctr0[4] = {first_free, 0ULL, 0ULL, 1ULL};   /* [3] low word: the plane flag, cleared by erk_init_kernel */
     if (!cuda_ok(cudaMemcpyAsync(ctr, ctr0, sizeof ctr0, cudaMemcpyHostToDevice, s), "H2D work counters")) return me->status = FLINT_ERROR;
     a.work_counter = ctr; a.counter_reset = first_free;
+    a.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
     const int grid_all = (int)((N + 127) / 128);
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -426,8 +435,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     g_launches += 1;
     if (le == cudaSuccess && !park) {
         a.list_in = nullptr; a.n_in = nullptr; a.list_out = nullptr; a.n_out = nullptr;
-        le = ke->step(a, (int)grid, block, s);
-        g_launches += 1;
+        if (try_plane) { le = ke->step_plane(a, (int)grid, block, s); g_launches += 1; }   /* returns at once unless the flag is set */
+        if (le == cudaSuccess) { le = ke->step(a, (int)grid, block, s); g_launches += 1; }
     } else if (le == cudaSuccess) {
         /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
          * parked count and stop when it is zero; asynchronous calls run a fixed schedule (empty kernels return
@@ -435,8 +444,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         const int max_rounds = ex.async ? 3 : 64;
         int cur = 1;                                               /* index of the counter of the list being filled */
         a.list_in = nullptr; a.n_in = nullptr; a.list_out = listA; a.n_out = ctr + 1;
-        le = ke->step_park(a, (int)grid, block, s);
-        g_launches += 1;
+        if (try_plane) { le = ke->step_plane(a, (int)grid, block, s); g_launches += 1; }
+        if (le == cudaSuccess) { le = ke->step_park(a, (int)grid, block, s); g_launches += 1; }
         for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
             long n_parked = N;
             if (!ex.async) {
@@ -464,8 +473,11 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 if (!cuda_ok(cudaMemcpyAsync(ctr, &ff, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) { le = cudaErrorUnknown; break; }
             }
             const bool last = round == max_rounds - 1;
-            le = (last ? ke->step : ke->step_park)(a, (int)g2, block, s);
-            g_launches += 1;
+            if (last) { a.zflag = nullptr; le = ke->step(a, (int)g2, block, s); g_launches += 1; }   /* in-loop events, general kernel */
+            else {
+                if (try_plane) { le = ke->step_plane(a, (int)g2, block, s); g_launches += 1; }
+                if (le == cudaSuccess) { le = ke->step_park(a, (int)g2, block, s); g_launches += 1; }
+            }
             cur = oth;
         }
     }
@@ -508,7 +520,7 @@ static ExecCtx make_exec(const flint_exec* x)
     if (x) {
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
-        e.event_mode = x->event_mode;
+        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant;
     }
     return e;
 }

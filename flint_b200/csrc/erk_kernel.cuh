@@ -427,7 +427,10 @@ __device__ __forceinline__ int state_load(const KArgs& p, long idx, Lane<SYS>& L
     const int flags = q[SI::FLAGS * c];
     L.X = d[D::X * c]; L.h = d[D::H * c]; L.hmax = d[D::HMAX * c]; L.hbyhoptOld = d[D::HOLD * c];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { L.Y[i] = d[(D::Y + i) * c]; L.F0[i] = d[(D::F0 + i) * c]; }
+    for (int i = 0; i < N; ++i) {
+        if (SYS::zc(i)) { L.Y[i] = 0.0; L.F0[i] = 0.0; }                 /* identically +0 (plane variant) */
+        else { L.Y[i] = d[(D::Y + i) * c]; L.F0[i] = d[(D::F0 + i) * c]; }
+    }
 #pragma unroll
     for (int i = 0; i < M; ++i) L.EV0[i] = d[(D::EV0 + i) * c];
     L.Xf = p.xf[idx];
@@ -473,6 +476,12 @@ __device__ __forceinline__ void store_results(const KArgs& p, long idx, const La
     if (DENSE && p.dense_count) p.dense_count[idx] = L.acc;
     p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
 }
+template <class SYS> __host__ __device__ constexpr bool is_plane_variant()
+{
+    for (int c = 0; c < SYS::N; ++c) if (SYS::zc(c)) return true;
+    return false;
+}
+
 template <class SYS>
 __device__ __forceinline__ bool keeps_going(const KArgs& p, const Lane<SYS>& L)
 {
@@ -498,6 +507,12 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
     for (int c = 0; c < N; ++c) { L.Y[c] = p.y0[(long)c * NN + idx]; L.F0[c] = 0.0; }
 #pragma unroll
     for (int i = 0; i < M; ++i) { L.EV0[i] = 0.0; L.EvDir[i] = 0; }
+    if (SYS::ZPLANE != 0u && p.zflag) {                                     /* every trajectory in the plane? (bitwise +0.0) */
+        bool in_plane = true;
+#pragma unroll
+        for (int c = 0; c < N; ++c) if ((SYS::ZPLANE >> c) & 1u) in_plane = in_plane && (__double_as_longlong(L.Y[c]) == 0LL);
+        if (!in_plane) *p.zflag = 0;
+    }
     L.Xf = p.xf[idx];
     L.total = 0; L.acc = 0; L.rej = 0; L.fcalls = 0; L.st = FLINT_SUCCESS;
     L.LAST = false; L.lastRej = false; L.stiffThr = 0; L.nonStiffThr = 0;
@@ -572,6 +587,8 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
     constexpr bool EVENTS = EVMODE != 0;
+    /* the plane variant and the general kernel are launched back to back; the flag erk_init_kernel left says which runs */
+    if (p.zflag && ((*p.zflag != 0) != is_plane_variant<SYS>())) return;
     SYS sys;
     sys.load(p.sp);
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;

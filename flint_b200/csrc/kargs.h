@@ -64,6 +64,7 @@ struct KArgs {
     const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */
     int* list_out; unsigned long long* n_out;    /* EVMODE 2: trajectories parked by this pass */
     unsigned long long counter_reset;            /* erk_event_kernel re-arms work_counter with this */
+    int* zflag;                                  /* NULL, or: 1 = every trajectory lies in the system's invariant plane (plane-variant kernel runs) */
     unsigned long long* work_counter;
     double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by launch_erk) */
 };
@@ -90,6 +91,7 @@ struct KernelEntry {
     launch_fn step;              /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
     launch_fn step_park;         /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
     launch_fn event;             /* erk_event_kernel (NULL when events == false) */
+    launch_fn step_plane;        /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
     occupancy_fn occupancy, occupancy_park;
     void (*load_coefficients)(double* dst);
     int n_state_doubles, n_state_ints;

@@ -16,6 +16,9 @@
  *     NOUT                       number of computed derivative components
  *     fsrc(c)                    f[c] = y[fsrc(c)] if >= 0; +0.0 if -1; out[-2 - fsrc(c)] otherwise
  *     accel<FMA>(in, out)        the computed components (branch-free division / square root, arith.cuh)
+ *     zc(c)                      component c is identically +0.0 in state and derivative (kernel variant for
+ *                                trajectories that live in an invariant coordinate plane; false in the general systems)
+ *     ZPLANE                     bit mask of the components a plane variant of this system may drop (0: none)
  *   rhs<FMA>(x, y, f)            F assembled from the above (eval_rhs, below)
  *   events(evset, x, y, eval_bits, value, dir, loc_event, action)   G
  * All four systems are autonomous (F does not read x).
@@ -71,6 +74,8 @@ struct SysCR3BPPlanar {
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
     static constexpr int NIN = 4, NOUT = 2;
+    static constexpr unsigned ZPLANE = (1u << 2) | (1u << 5);   /* z = vz = 0 is invariant under F and under every event action below */
+    __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i < 2 ? i : i + 1; }          /* y0 y1 y3 y4 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : (c == 5 ? -1 : -2 - (c - 3)); }
 
@@ -130,6 +135,14 @@ struct SysCR3BPPlanar {
     }
 };
 
+/* Planar CR3BP for trajectories whose z and vz are exactly +0.0: both stay +0.0 through every stage
+ * ((+0) + h*(+-0) = +0, f[2] = y[5], f[5] = 0), contribute (+-0/Sc)^2 = +0 to the error norms, and no event
+ * action of this system moves them, so the integrator may drop the two components without changing a bit
+ * of any result.  erk_init_kernel checks the condition per trajectory; the generic kernel runs otherwise. */
+struct SysCR3BPPlanarZ : SysCR3BPPlanar {
+    __host__ __device__ static constexpr bool zc(int c) { return c == 2 || c == 5; }
+};
+
 /* ---- spatial CR3BP: tests/test_WP.f90:88-109 (no events in the reference) ---- */
 struct SysCR3BPSpatial {
     static constexpr int N = 6;
@@ -139,6 +152,8 @@ struct SysCR3BPSpatial {
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
     static constexpr int NIN = 5, NOUT = 3;
+    static constexpr unsigned ZPLANE = 0;
+    __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y4 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
 
@@ -186,6 +201,8 @@ struct SysLorenz {
     __device__ __forceinline__ void load(const double* sp) { sigma = sp[0]; rho = sp[1]; beta = sp[2]; }
 
     static constexpr int NIN = 3, NOUT = 3;
+    static constexpr unsigned ZPLANE = 0;
+    __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }
     __host__ __device__ static constexpr int fsrc(int c) { return -2 - c; }
 
@@ -210,6 +227,8 @@ struct SysTwoBody {
     __device__ __forceinline__ void load(const double* sp) { GM = sp[0]; }
 
     static constexpr int NIN = 3, NOUT = 3;
+    static constexpr unsigned ZPLANE = 0;
+    __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* position */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
 

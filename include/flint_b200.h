@@ -143,6 +143,9 @@ typedef struct {
     int event_mode;     /* how accepted steps with an event to locate are handled: 0 = automatic, 1 = inside the
                            stepping kernel, 2 = parked and located in batches by a separate kernel (the default
                            choice unless an unmasked event has an EventStepSz).  Results are identical. */
+    int plane_variant;  /* 0 = automatic: ensembles whose trajectories all lie in an invariant coordinate plane of the
+                           system (planar CR3BP with z = vz = +0) run a kernel that drops the identically-zero
+                           components; 2 = never.  Results are identical. */
 } flint_exec;
 
 /* ---- DiffEqSys ---- */

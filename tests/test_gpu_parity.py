@@ -110,6 +110,25 @@ def test_event_modes_are_equivalent(event_mode):
 
 @pytest.mark.parametrize("arith", [0, 1])
 @pytest.mark.parametrize("method", METHODS)
+def test_plane_variant_is_bit_identical(method, arith):
+    """Planar CR3BP ensembles with z = vz = +0 run the kernel that drops the two identically-zero components
+    (automatic); forcing the general kernel (plane_variant=2) and the oracle give the same bits.  An ensemble with
+    one out-of-plane orbit, or with a -0.0, must take the general kernel by itself."""
+    for eventset in (F.FLINT_EVSET_NONE, F.FLINT_EVSET_CR3BP_SAMPLE3, F.FLINT_EVSET_XY_CROSSING):
+        case = K.cr3bp_case(method, 1e-10, arith, norb=1.2, eventset=eventset)
+        y0 = P.cr3bp_ensemble(300, start=2500)
+        o = case.run_oracle(y0)
+        K.compare_batch(case.run_gpu(y0), o, case, "plane auto evset %d" % eventset)
+        K.compare_batch(case.run_gpu(y0, plane_variant=2), o, case, "plane off evset %d" % eventset)
+    case = K.cr3bp_case(method, 1e-10, arith, norb=1.2)
+    y0 = P.cr3bp_ensemble(300, start=2500)
+    y0[2, 17] = 1e-3
+    y0[5, 99] = -0.0
+    K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "out of plane")
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("method", METHODS)
 def test_lorenz_no_events(method, arith):
     case = K.lorenz_case(method, 1e-11, arith, xf=10.0)
     y0 = P.lorenz_ensemble(512)

@@ -216,6 +216,8 @@ def stage_sums(E, P, row, dest, lead_zero, keep_zero_terms=False, save_sum=None,
     E("#pragma unroll")
     E("for (int c = 0; c < N; ++c) {")
     E.ind += 1
+    # a component whose state AND derivative are identically +0.0 (SYS::zc) stays +0.0: (+0) + h*(+-0) = +0
+    E("if (SYS::zc(c)) { %s[c] = 0.0; %scontinue; }" % (dest, ("%s[c] = 0.0; " % save_sum) if save_sum else ""))
     emit_sum(E, [(P.k(j), P.a[aidx(row, j)]) for j in range(1, row)], lead_zero, keep_zero_terms)
     if save_sum:
         E("%s[c] = acc;" % save_sum)
@@ -224,70 +226,67 @@ def stage_sums(E, P, row, dest, lead_zero, keep_zero_terms=False, save_sum=None,
     E("}")
 
 
-SC_BLOCK = ["double sc[N];", "#pragma unroll", "for (int c = 0; c < N; ++c)",
-            "    sc[c] = madd<FMA>(tol.rt(c), dmax(fabs(Y0[c]), fabs(Ynew[c])), tol.at(c));"]
-
-
 def emit_error(E, P):
-    """error norm into Err (estimate == true path).  The n (DOP853: 2n) quotients by Sc are formed with
-    one refined reciprocal per component and no branches (arith.cuh: div_rcp_z); a failed range test
-    redoes them with the plain operator out of line."""
+    """error norm into Err (estimate == true path).
+
+    The quotients by Sc are formed without branches: one refined reciprocal per component
+    (arith.cuh: rcp_newton, div_rcp_nochk) and a range test that needs only Sc and the size of the
+    quotient, because only q*q is used: a quotient below 2^-600 squares to +0 whatever its last bits or
+    sign.  A failed test redoes all quotients with the plain operator out of line.  Components whose state and
+    derivative are identically +0 (SYS::zc) contribute (+-0/Sc)^2 = +0 and are skipped (the host selects such a
+    kernel only when ATol > 0 there, so Sc > 0); components with a structurally zero derivative (fsrc == -1)
+    contribute +0 when Sc is positive and finite, else what 0/Sc gives."""
     M = P.M
-    for ln in SC_BLOCK:
-        E(ln)
-    E("double isc[N];")
-    E("#pragma unroll")
-    E("for (int c = 0; c < N; ++c) isc[c] = rcp_newton(sc[c]);")
+    E("static_assert(!SYS::zc(0), \"component 0 starts the error sums\");")
     E("bool qok = true;")
+    E("VecN<N> scv;")
     if M == "DOP853":
-        E("VecN<N> t5, t3;")
-        E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) {")
-        E.ind += 1
+        E("VecN<N> t5, t3, q5, q3;")
+    else:
+        E("VecN<N> tn, qn;")
+    E("#pragma unroll")
+    E("for (int c = 0; c < N; ++c) {")
+    E.ind += 1
+    if M == "DOP853":
+        E("if (SYS::zc(c)) { scv.v[c] = 1.0; t5.v[c] = t3.v[c] = q5.v[c] = q3.v[c] = 0.0; continue; }")
+    else:
+        E("if (SYS::zc(c)) { scv.v[c] = 1.0; tn.v[c] = qn.v[c] = 0.0; continue; }")
+    E("const double sc = madd<FMA>(tol.rt(c), dmax(fabs(Y0[c]), fabs(Ynew[c])), tol.at(c));")
+    E("scv.v[c] = sc;")
+    if M == "DOP853":
         emit_sum(E, [(P.k(j + 1), P.e[j]) for j in range(P.sint)], lead_zero=False, var="t")
         E("t5.v[c] = t;")
         E("double u = madd<FMA>(%s, %s, bsum[c]);" % (cx(-P.bhh[0]), P.k(1)))
         E("u = madd<FMA>(%s, %s, u);" % (cx(-P.bhh[1]), P.k(9)))
         E("u = madd<FMA>(%s, %s, u);" % (cx(-P.bhh[2]), P.k(12)))
         E("t3.v[c] = u;")
-        E.ind -= 1
-        E("}")
-        E("VecN<N> q5, q3;")
-        E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) { q5.v[c] = div_rcp_z(t5.v[c], sc[c], isc[c], qok); q3.v[c] = div_rcp_z(t3.v[c], sc[c], isc[c], qok); }")
-        E("if (!qok) {")
-        E("    VecN<N> scv;")
-        E("#pragma unroll")
-        E("    for (int c = 0; c < N; ++c) scv.v[c] = sc[c];")
-        E("    q5 = quotients_plain<N>(t5, scv); q3 = quotients_plain<N>(t3, scv);")
-        E("}")
+        E("if (SYS::fsrc(c) == -1) { q5.v[c] = q3.v[c] = zero_over(sc); continue; }")
+        E("const double isc = rcp_newton(sc);")
+        E("q5.v[c] = div_rcp_nochk(t, sc, isc); q3.v[c] = div_rcp_nochk(u, sc, isc);")
+        E("qok = qok & moderate(sc) & below_2p600(q5.v[c]) & below_2p600(q3.v[c]);")
+    else:
+        emit_sum(E, [(P.k(j + 1), P.e[j]) for j in range(P.sint)], lead_zero=P.generic, var="t")
+        E("tn.v[c] = h * t;")
+        E("if (SYS::fsrc(c) == -1) { qn.v[c] = zero_over(sc); continue; }")
+        E("qn.v[c] = div_rcp_nochk(tn.v[c], sc, rcp_newton(sc));")
+        E("qok = qok & moderate(sc) & below_2p600(qn.v[c]);")
+    E.ind -= 1
+    E("}")
+    if M == "DOP853":
+        E("if (!qok) { q5 = quotients_plain<N>(t5, scv); q3 = quotients_plain<N>(t3, scv); }")
         E("double Es = 0.0, E3 = 0.0;")
         E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) Es = (c == 0) ? __dmul_rn(q5.v[c], q5.v[c]) : madd<FMA>(q5.v[c], q5.v[c], Es);")
+        E("for (int c = 0; c < N; ++c) if (!SYS::zc(c)) Es = (c == 0) ? __dmul_rn(q5.v[c], q5.v[c]) : madd<FMA>(q5.v[c], q5.v[c], Es);")
         E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) E3 = (c == 0) ? __dmul_rn(q3.v[c], q3.v[c]) : madd<FMA>(q3.v[c], q3.v[c], E3);")
+        E("for (int c = 0; c < N; ++c) if (!SYS::zc(c)) E3 = (c == 0) ? __dmul_rn(q3.v[c], q3.v[c]) : madd<FMA>(q3.v[c], q3.v[c], E3);")
         E("double den = madd<FMA>(0.01, E3, Es);")
         E("if (den == 0.0) den = 1.0;")
         E("Err = (fabs(h) * Es) * sqrt(1.0 / ((double)N * den));")
     else:
-        E("VecN<N> tn, qn;")
-        E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) {")
-        E.ind += 1
-        emit_sum(E, [(P.k(j + 1), P.e[j]) for j in range(P.sint)], lead_zero=P.generic, var="t")
-        E("tn.v[c] = h * t;")
-        E("qn.v[c] = div_rcp_z(tn.v[c], sc[c], isc[c], qok);")
-        E.ind -= 1
-        E("}")
-        E("if (!qok) {")
-        E("    VecN<N> scv;")
-        E("#pragma unroll")
-        E("    for (int c = 0; c < N; ++c) scv.v[c] = sc[c];")
-        E("    qn = quotients_plain<N>(tn, scv);")
-        E("}")
+        E("if (!qok) qn = quotients_plain<N>(tn, scv);")
         E("double sm = 0.0;")
         E("#pragma unroll")
-        E("for (int c = 0; c < N; ++c) sm = (c == 0) ? __dmul_rn(qn.v[c], qn.v[c]) : madd<FMA>(qn.v[c], qn.v[c], sm);")
+        E("for (int c = 0; c < N; ++c) if (!SYS::zc(c)) sm = (c == 0) ? __dmul_rn(qn.v[c], qn.v[c]) : madd<FMA>(qn.v[c], qn.v[c], sm);")
         E("Err = sqrt(sm / (double)N);")
 
 
@@ -329,6 +328,7 @@ def emit_iteration_pre(E, P, it, kind, st):
             E("#pragma unroll")
             E("for (int c = 0; c < N; ++c) {")
             E.ind += 1
+            E("if (SYS::zc(c)) { Ynew[c] = 0.0; continue; }")
             emit_sum(E, [(P.k(j + 1), P.b[j]) for j in range(sint)], lead_zero=True)
             E("Ynew[c] = madd<FMA>(h, acc, Y0[c]);")
             E.ind -= 1
