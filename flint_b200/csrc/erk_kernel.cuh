@@ -114,6 +114,56 @@ __device__ __forceinline__ void brent_root(double a, double b, double ya, double
     niter = itr;
 }
 
+/* ---- stage-vector store.  Generated code reads k_j[c] as ks.get<slot>(c) and writes a whole vector with
+ * ks.put<slot>(f).  Slots in SMEM_MASK live in shared memory ([slot][component][thread]: conflict-free, the
+ * offset is an immediate), the others in registers.  Why: at a right-hand-side call the caller holds ~10 live
+ * stage vectors, which leaves the callee too few registers to run its two square-root and reciprocal chains
+ * in lock step -- ptxas then serialises ~68 dependent fp64 operations of 8 cycles each
+ * (profiles/r01_notes.md).  Components that are structurally +0 are never stored. ---- */
+template <class SYS> __host__ __device__ constexpr bool comp_stored(int c) { return !SYS::zc(c) && SYS::fsrc(c) != -1; }
+template <class SYS> __host__ __device__ constexpr int comp_rank(int c)
+{
+    int r = 0;
+    for (int i = 0; i < c; ++i) if (comp_stored<SYS>(i)) ++r;
+    return r;
+}
+template <class SYS> __host__ __device__ constexpr int comps_stored() { return comp_rank<SYS>(SYS::N); }
+__host__ __device__ constexpr int slot_rank(unsigned mask, int slot)
+{
+    int r = 0;
+    for (int i = 0; i < slot; ++i) if ((mask >> i) & 1u) ++r;
+    return r;
+}
+template <class METHOD, class SYS, unsigned SMEM_MASK>
+struct KStore {
+    static constexpr int N = SYS::N, NC = comps_stored<SYS>();
+    double r[METHOD::NSLOT][N];
+    volatile double* s;                          /* this thread's column of the dynamic shared memory; volatile: every get is a load
+                                                    (otherwise the compiler forwards the stored registers and nothing is saved) */
+    template <int SLOT> __device__ __forceinline__ double get(int c) const
+    {
+        if (!comp_stored<SYS>(c)) return 0.0;
+        if constexpr ((SMEM_MASK >> SLOT) & 1u) return s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * FLINT_BLOCK_THREADS];
+        else return r[SLOT][c];
+    }
+    template <int SLOT> __device__ __forceinline__ void put(const double (&v)[N])
+    {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            if (!comp_stored<SYS>(c)) continue;
+            if constexpr ((SMEM_MASK >> SLOT) & 1u) s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * FLINT_BLOCK_THREADS] = v[c];
+            else r[SLOT][c] = v[c];
+        }
+    }
+    template <int SLOT> __device__ __forceinline__ void load(double (&v)[N]) const
+    {
+#pragma unroll
+        for (int c = 0; c < N; ++c) v[c] = get<SLOT>(c);
+    }
+};
+template <class METHOD, class SYS, unsigned SMEM_MASK>
+constexpr int kstore_smem_bytes() { return slot_rank(SMEM_MASK, 32) * comps_stored<SYS>() * FLINT_BLOCK_THREADS * 8; }
+
 /* ---- context of the rare event path (lives in local memory) ---- */
 template <class METHOD, class SYS>
 struct EvCtx {
@@ -141,7 +191,9 @@ __device__ __forceinline__ void remat_bip(const SYS& sys, const KArgs& p, EvCtx<
 {
     if (c.haveB) return;
     constexpr int N = SYS::N;
-    double ks[METHOD::NSLOT][N], Yn[N], Yp[N], e;
+    KStore<METHOD, SYS, 0u> ks;
+    ks.s = nullptr;
+    double Yn[N], Yp[N], e;
     METHOD::template step<SYS, FMA, true>(sys, c.X, c.Y, c.F0old, c.h_stage, c.h, ks, Yn, Yp, p.tol, false, e, p.coef);
     METHOD::template dense_coeffs<SYS, FMA>(ks, c.Y, c.h, c.Y1, c.B, p.coef);
     c.haveB = true;
@@ -612,6 +664,9 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 #pragma unroll
     for (int i = 0; i < M; ++i) { L.EV0[i] = 0; L.EvDir[i] = 0; }
     EvCtx<METHOD, SYS> ctx;                 /* EVMODE 1 only: local memory, touched when an event has to be located */
+    extern __shared__ double flint_smem[];
+    KStore<METHOD, SYS, METHOD::SMEM_SLOTS> ks;
+    ks.s = flint_smem + threadIdx.x;
 
     for (;;) {
         /* ---------------- refill: take the next trajectory from the state block ---------------- */
@@ -652,7 +707,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         if (have) {
             if (L.hSign * (madd<FMA>(fac, L.h, L.X) - L.Xf) > 0.0) { L.h = L.Xf - L.X; L.LAST = true; }   /* :268-271 */
             const double h = L.h;
-            double ks[METHOD::NSLOT][N], Ynew[N], Ypre[N], Err;
+            double Ynew[N], Ypre[N], Err;
             METHOD::template step<SYS, FMA, DENSE>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
             L.total += 1;
             double hbyhopt = 1.0;
@@ -670,7 +725,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                         double dk[N], dy[N];
 #pragma unroll
                         for (int c = 0; c < N; ++c) {
-                            dk[c] = ks[METHOD::SLOT_KSINT][c] - ks[METHOD::SLOT_KSINT_M1][c];
+                            dk[c] = ks.template get<METHOD::SLOT_KSINT>(c) - ks.template get<METHOD::SLOT_KSINT_M1>(c);
                             dy[c] = (METHOD::YSINT_ASSIGNED ? Ynew[c] : 0.0) - Ypre[c];
                         }
                         const double sN = norm2<FMA, N>(dk), sD = norm2<FMA, N>(dy);
@@ -710,7 +765,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 #pragma unroll
                             for (int i = 0; i < N; ++i) {
                                 ctx.Y[i] = L.Y[i]; ctx.Y1[i] = Ynew[i]; ctx.F0old[i] = L.F0[i]; ctx.ENY[i] = yy[i];
-                                ctx.F0new[i] = ks[METHOD::SLOT_F0NEW][i];
+                                ctx.F0new[i] = ks.template get<METHOD::SLOT_F0NEW>(i);
                             }
 #pragma unroll
                             for (int i = 0; i < M; ++i) { ctx.EV0[i] = L.EV0[i]; ctx.EV1[i] = EV1[i]; ctx.EvDir[i] = L.EvDir[i]; }
@@ -726,7 +781,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                             double* d = p.sd + idx;
                             d[D::HSTEP * c] = h; d[D::ERR * c] = Err; d[D::HBH * c] = hbyhopt;
 #pragma unroll
-                            for (int i = 0; i < N; ++i) { d[(D::Y1 + i) * c] = Ynew[i]; d[(D::F0N + i) * c] = ks[METHOD::SLOT_F0NEW][i]; }
+                            for (int i = 0; i < N; ++i) { d[(D::Y1 + i) * c] = Ynew[i]; d[(D::F0N + i) * c] = ks.template get<METHOD::SLOT_F0NEW>(i); }
 #pragma unroll
                             for (int i = 0; i < M; ++i) d[(D::EV1 + i) * c] = EV1[i];
                             p.si[SI::DET * c + idx] = (int)det; p.si[SI::SS * c + idx] = (int)ss;
@@ -741,9 +796,10 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 if (!rare) {
                     double B[PS + 1][N];       /* dead unless DENSE */
                     if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, L.Y, h, Ynew, B, p.coef);
-                    double hio = h;
+                    double hio = h, F0new[N];
+                    ks.template load<METHOD::SLOT_F0NEW>(F0new);
                     commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
-                                                                 L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, ks[METHOD::SLOT_F0NEW], Err, hbyhopt,
+                                                                 L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, F0new, Err, hbyhopt,
                                                                  bip_counted, Ynew, B);
                     L.h = hio;
                 }
@@ -809,7 +865,13 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
 template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
 cudaError_t launch_step(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE><<<grid, block, 0, s>>>(a);
+    constexpr int smem = kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>();
+    if (smem > 0 && block != FLINT_BLOCK_THREADS) return cudaErrorInvalidConfiguration;   /* the shared-memory layout is compiled for this block size */
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <class METHOD, class SYS, bool FMA, bool DENSE>
@@ -827,7 +889,8 @@ cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
 template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
 cudaError_t occupancy_step(int* blocks_per_sm, int block)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, block, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, block,
+                                                         kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>());
 }
 template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }
 

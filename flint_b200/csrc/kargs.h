@@ -11,6 +11,24 @@
 #ifndef FLINT_MIN_BLOCKS
 #define FLINT_MIN_BLOCKS 4
 #endif
+/* stage-vector slots of each method that the hot kernel keeps in shared memory (bit i = slot i); tuning knobs */
+#ifndef FLINT_SMEM_SLOTS_DOP853
+#define FLINT_SMEM_SLOTS_DOP853 0u
+#endif
+#ifndef FLINT_SMEM_SLOTS_DOP54
+#define FLINT_SMEM_SLOTS_DOP54 0u
+#endif
+#ifndef FLINT_SMEM_SLOTS_VERNER98R
+#define FLINT_SMEM_SLOTS_VERNER98R 0u
+#endif
+#ifndef FLINT_SMEM_SLOTS_VERNER65E
+#define FLINT_SMEM_SLOTS_VERNER65E 0u
+#endif
+/* which out-of-line copy of the right-hand side stage-iteration `it` of `n` calls (arith.cuh: accel_call) */
+#ifndef FLINT_RHS_SPLIT
+#define FLINT_RHS_SPLIT 0            /* stage iterations below this index call copy 1, the rest copy 0 */
+#endif
+#define FLINT_RHS_COPY(it, n) ((it) < FLINT_RHS_SPLIT ? 1 : 0)
 #ifndef FLINT_SYNC_BLOCK
 #define FLINT_SYNC_BLOCK 1
 #endif

@@ -91,9 +91,10 @@ struct SysCR3BPPlanar {
         s2 = madd<FMA>(y1, y1, s2);
         const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1;
         const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4);
-        const double n1 = sqrt_nochk(s1), n2 = sqrt_nochk(s2);
+        double n1, n2, i1, i2;
+        sqrt2_nochk(s1, s2, n1, n2);
         const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
-        const double i1 = rcp_newton(r1c), i2 = rcp_newton(r2c);
+        rcp2_newton(r1c, r2c, i1, i2);
         double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
         double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
         if (!ok) {                                   /* operands outside the fast-path range: plain operators, out of line */
@@ -172,9 +173,10 @@ struct SysCR3BPSpatial {
         const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1, u5 = -omm * y2, u6 = mu * y2;
         const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4) & moderate(u5) &
                         moderate(u6);
-        const double n1 = sqrt_nochk(s1), n2 = sqrt_nochk(s2);
+        double n1, n2, i1, i2;
+        sqrt2_nochk(s1, s2, n1, n2);
         const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
-        const double i1 = rcp_newton(r1c), i2 = rcp_newton(r2c);
+        rcp2_newton(r1c, r2c, i1, i2);
         double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
         double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
         double q5 = div_rcp_nochk(u5, r1c, i1), q6 = div_rcp_nochk(u6, r2c, i2);

@@ -181,7 +181,7 @@ class Plan:
         self.slot, self.nslot = slot, nslot
 
     def k(self, j):
-        return "ks[%d][c]" % self.slot[j]
+        return "ks.template get<%d>(c)" % self.slot[j]
 
 
 def emit_sum(E, terms, lead_zero, keep_zero_terms=False, var="acc"):
@@ -372,6 +372,8 @@ def gen_method(E_out, S, M):
     E("/* stage vectors live in NSLOT register slots (liveness-based reuse): stage -> slot")
     E(" *   " + ", ".join("k%d->%d" % (j, P.slot[j]) for j in sorted(P.slot) if j > 0) + (", F0next->%d" % P.slot[0] if 0 in P.slot else "") + " */")
     E("static constexpr int NSLOT = %d;" % P.nslot)
+    E("/* slots the hot kernel keeps in shared memory instead of registers (erk_kernel.cuh: KStore) */")
+    E("static constexpr unsigned SMEM_SLOTS = FLINT_SMEM_SLOTS_%s;" % U)
     E("static constexpr int NIT = %d, NIT_DENSE = %d;   /* loop iterations: integration / with dense stages */" % (P.n_int, n_all))
     E("static constexpr int SLOT_KSINT = %d, SLOT_KSINT_M1 = %d;   /* CheckStiffness operands */" % (P.slot[sint], P.slot[sint - 1]))
     f0new_stage = {"DOP853": 13, "DOP54": 7, "Verner65E": sint, "Verner98R": 0}[M]
@@ -386,9 +388,9 @@ def gen_method(E_out, S, M):
     E(" * Out: ks (stage vectors), Ynew (candidate), Ypre (state of stage sint-1, for CheckStiffness),")
     E(" * Err (0 when !estimate).  The evaluation at (X0+h, Ynew) is always made (it is the next F0")
     E(" * when the step is accepted and costs 1/%d of the attempt when it is not). */" % (P.n_int))
-    E("template <class SYS, bool FMA, bool DENSE>")
+    E("template <class SYS, bool FMA, bool DENSE, class KS>")
     E("static __device__ __forceinline__ void step(const SYS& sys, double X0, const double (&Y0)[SYS::N], const double (&F0)[SYS::N],")
-    E("        double h, double hd, double (&ks)[NSLOT][SYS::N], double (&Ynew)[SYS::N], double (&Ypre)[SYS::N], const Tol& tol,")
+    E("        double h, double hd, KS& ks, double (&Ynew)[SYS::N], double (&Ypre)[SYS::N], const Tol& tol,")
     E("        bool estimate, double& Err, const double (&C)[FLINT_NCOEF])")
     E("{")
     E.ind += 1
@@ -399,7 +401,8 @@ def gen_method(E_out, S, M):
     if M == "DOP853":
         E("double bsum[N];")
     E("#pragma unroll")
-    E("for (int c = 0; c < N; ++c) { ks[0][c] = F0[c]; yt[c] = Y0[c]; }")
+    E("for (int c = 0; c < N; ++c) yt[c] = Y0[c];")
+    E("ks.template put<0>(F0);")
     E("Err = 0.0;")
     E("constexpr int nit = DENSE ? NIT_DENSE : NIT;")
     if UNROLLED:
@@ -410,7 +413,7 @@ def gen_method(E_out, S, M):
             E("{   /* %s */" % (("stage %d" % st) if kind == "stage" else "evaluation at (X0+h, Ynew)"))
             E.ind += 1
             emit_iteration_pre(E, P, it, kind, st)
-            E("rhs_eval<SYS, FMA>(sys, yt, ks[%d]);" % P.slot[st])
+            E("{ double fv[N]; rhs_eval<SYS, FMA, FLINT_RHS_COPY(%d, %d)>(sys, yt, fv); ks.template put<%d>(fv); }" % (it, len(P.its), P.slot[st]))
             E.ind -= 1
             E("}")
         if len(P.its) > P.n_int:
@@ -434,7 +437,7 @@ def gen_method(E_out, S, M):
         for it, (kind, st) in enumerate(P.its):
             E("case %d:" % it)
             E("#pragma unroll")
-            E("    for (int c = 0; c < N; ++c) ks[%d][c] = f[c];" % P.slot[st])
+            E("    ks.template put<%d>(f);" % P.slot[st])
             E("    break;")
         E("default: break;")
         E("}")
@@ -456,8 +459,8 @@ def gen_method(E_out, S, M):
     d, dinz = P.d, P.dinz
     rows = d["shape"][0]
     E("/* Dense-output coefficients B[j][c] of theta^j, j = 0..PSTAR (all n states), from the stage vectors. */")
-    E("template <class SYS, bool FMA>")
-    E("static __device__ __forceinline__ void dense_coeffs(const double (&ks)[NSLOT][SYS::N], const double (&Y0)[SYS::N], double h,")
+    E("template <class SYS, bool FMA, class KS>")
+    E("static __device__ __forceinline__ void dense_coeffs(const KS& ks, const double (&Y0)[SYS::N], double h,")
     E("        const double (&Y1)[SYS::N], double (&B)[PSTAR + 1][SYS::N], const double (&C)[FLINT_NCOEF])")
     E("{")
     E.ind += 1
