@@ -36,6 +36,15 @@ struct flint_sys {
     double sp[8];
 };
 
+struct DevCache {                      /* device staging buffers kept between calls (see DevBuf) */
+    int device = -1;
+    std::vector<void*> ptr;
+    std::vector<size_t> size;
+    void release() { for (void* p : ptr) if (p) cudaFree(p); ptr.clear(); size.clear(); device = -1; }
+};
+
+struct ScopedCache : DevCache { ~ScopedCache() { release(); } };
+
 struct Workspace {                     /* trajectory state block + work lists of Integrate; grows, never shrinks */
     int device = -1;
     size_t bytes = 0;
@@ -82,6 +91,7 @@ struct flint_erk {
     /* dense storage */
     DenseStore dense;
     Workspace ws;
+    DevCache stage_int;
     bool dense_is_scalar = false;
     bool dense_allocated = false;      /* allocated(me%Xint) */
 };
@@ -144,6 +154,7 @@ extern "C" void flint_erk_destroy(flint_erk_t* e)
     if (!e) return;
     e->dense.release();
     e->ws.release();
+    e->stage_int.release();
     delete e;
 }
 
@@ -234,15 +245,24 @@ extern "C" int flint_erk_init(flint_erk_t* me, const flint_sys_t* DE, int max_st
 /* ------------------------------------------------------------------ Integrate */
 namespace {
 
-struct DevBuf {                        /* RAII device scratch for FLINT_MEM_HOST staging */
-    std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+/* Device staging buffers of the FLINT_MEM_HOST path, cached in the handle: the k-th allocation of a call reuses the
+ * k-th buffer of the previous call when it is large enough (cudaMalloc/cudaFree of ~100 MB buffers cost milliseconds
+ * and cudaFree synchronises the device). */
+struct DevBuf {
+    DevCache& c;
+    size_t k = 0;
+    DevBuf(DevCache& cache, int device) : c(cache) { if (c.device != device) { c.release(); c.device = device; } }
     template <class T> T* alloc(size_t count)
     {
-        void* p = nullptr;
-        if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        ptrs.push_back(p);
-        return (T*)p;
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (k >= c.ptr.size()) { c.ptr.push_back(nullptr); c.size.push_back(0); }
+        if (c.size[k] < bytes) {
+            if (c.ptr[k]) cudaFree(c.ptr[k]);
+            c.ptr[k] = nullptr; c.size[k] = 0;
+            if (cudaMalloc(&c.ptr[k], bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            c.size[k] = bytes;
+        }
+        return (T*)c.ptr[k++];
     }
 };
 
@@ -318,7 +338,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     a.ev_cap = events_on ? events->cap : 0;
     a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
 
-    DevBuf scratch;
+    DevBuf scratch(me->stage_int, ex.device);
     cudaStream_t s = ex.stream;
     const size_t szN = (size_t)N;
     /* ---- device views of the caller's buffers ---- */
@@ -586,7 +606,8 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     if (!cuda_ok(cudaSetDevice(D.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const long N = D.N;
     cudaStream_t s = ex.stream;
-    DevBuf scratch;
+    ScopedCache scoped;                      /* Yarr can be most of the device memory: not kept between calls */
+    DevBuf scratch(scoped, D.device);
     /* monotonicity of the shared grid is a host-side check (:60-68) */
     std::vector<double> hx;
     const double* xh = xarr;
