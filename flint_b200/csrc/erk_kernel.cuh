@@ -357,15 +357,29 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, bool event
     const bool const_step = p.const_step != 0;
     if constexpr (DENSE) {                                              /* :555-566 */
         if (!bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }
-        if (acc <= p.dense_cap) {
-            p.dxint[(long)acc * NN + idx] = X + h;
-            for (int j = 0; j <= PS; ++j)
-                for (int ii = 0; ii < p.nI; ++ii) {
-                    double v = 0.0;
+        if (acc <= p.dense_cap) {          /* per-trajectory runs: dxint[N][cap+1], dbip[N][cap][pstar+1][nI] (interp_kernel.cu) */
+            p.dxint[idx * (p.dense_cap + 1) + acc] = X + h;
+            double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)((PS + 1) * p.nI);
+            if (p.nI == N) {               /* all states, in order (the default): the record is B itself */
+                if (((PS + 1) * N) % 2 == 0) {
 #pragma unroll
-                    for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
-                    p.dbip[(((long)j * p.nI + ii) * p.dense_cap + (acc - 1)) * NN + idx] = v;
+                    for (int q = 0; q < (PS + 1) * N / 2; ++q)
+                        reinterpret_cast<double2*>(rec)[q] = make_double2(B[(2 * q) / N][(2 * q) % N], B[(2 * q + 1) / N][(2 * q + 1) % N]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j <= PS; ++j)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) rec[j * N + c] = B[j][c];
                 }
+            } else {
+                for (int j = 0; j <= PS; ++j)
+                    for (int ii = 0; ii < p.nI; ++ii) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
+                        rec[j * p.nI + ii] = v;
+                    }
+            }
         }
     }
     if (EVENTS && eventsOn) {                                           /* :572-582 (quirks Q4, Q5) */
@@ -626,7 +640,7 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
 #pragma unroll
         for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + 0) * NN + idx] = L.Y[c];
     }
-    if (DENSE && p.dense_cap > 0) p.dxint[0 * NN + idx] = L.X;              /* :259 */
+    if (DENSE && p.dense_cap > 0) p.dxint[idx * (p.dense_cap + 1)] = L.X;   /* :259 */
     if (!keeps_going<SYS>(p, L)) store_results<SYS, DENSE>(p, idx, L);
     else state_store<SYS>(p, idx, L, 0);
 }

@@ -94,8 +94,9 @@ struct InterpArgs {
     const double* dxint; const double* dbip; const int* dcount;
     const double* xarr;
     double* yarr; int layout;        /* 0: [N][G][nI], 1: [nI][G][N] */
-    int* status;                     /* [N] or NULL */
+    int* status;                     /* [N] */
     int fma;
+    long chunk; int nchunks;         /* filled by launch_interp */
 };
 cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
 

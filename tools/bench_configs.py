@@ -1,0 +1,95 @@
+#!/usr/bin/env python3
+"""Secondary measurements on one GPU: BASELINE.json configs 2, 4 and 5.  Prints one JSON line per
+measurement (inputs resident in HBM, CUDA-event timing through the library's own kernel timer, best of `reps`).
+
+    python tools/bench_configs.py [lorenz] [dense] [wp] [--small]
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import flint_b200 as F
+from flint_b200 import problems as P
+
+small = "--small" in sys.argv
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["lorenz", "dense", "wp"]
+peak_tf, _ = F.measure_fp64_peak(0)
+HBM_GBS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6548.8
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def run(erk, x0, y0, xf, reps=2, **kw):
+    best, r = 1e30, None
+    for _ in range(reps):
+        r = erk.IntegrateBatch(x0, y0, xf, StepSz=0.0, **kw)
+        best = min(best, r["kernel_ms"])
+    return best, r
+
+
+if "lorenz" in which:      # config 2: Lorenz, 2^20 perturbed ICs, DOP54, rtol 1e-11 atol 1e-14, x in [0,100], no events
+    N = 1 << (16 if small else 20)
+    for arith in (0, 1):
+        sys_ = F.DiffEqSys(F.FLINT_SYS_LORENZ, F.FLINT_EVSET_NONE, list(P.LORENZ_PARAMS))
+        erk = F.ERK()
+        assert erk.Init(sys_, 100000, Method=F.ERK_DOP54, ATol=[1e-14], RTol=[1e-11], Arith=arith) == 0
+        y0 = torch.from_numpy(P.lorenz_ensemble(N)).cuda()
+        ms, r = run(erk, 0.0, y0, 100.0, StiffTest=0)
+        cnt = r["counters"].cpu().numpy().astype(np.int64)
+        fl = P.algorithmic_flops(F.ERK_DOP54, F.FLINT_SYS_LORENZ, 3, cnt[0].sum(), cnt[1].sum())
+        emit(config=2, what="Lorenz DOP54 trajectories/s", arith=arith, N=N, ms=ms, value=N / ms * 1e3, unit="trajectories/s",
+             attempts_per_traj=float(cnt[0].mean()), tflops_alg=fl / ms / 1e9, frac_fp64_peak=fl / ms / 1e9 / peak_tf,
+             ok=float((r["status"] == 0).float().mean()))
+
+if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolation onto a shared uniform grid
+    N = 1 << (14 if small else 17)
+    G = 10000
+    for arith in (0, 1):
+        sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
+        y0 = torch.from_numpy(P.cr3bp_ensemble(N)).cuda()
+        ms, r = run(erk, 0.0, y0, xf, reps=1, dense_cap=640, **ikw)
+        cnt = r["counters"].cpu().numpy().astype(np.int64)
+        fl = P.algorithmic_flops(F.ERK_VERNER98R, F.FLINT_SYS_CR3BP_PLANAR, 6, cnt[0].sum(), cnt[1].sum(), cnt[1].sum())
+        emit(config=4, what="CR3BP Verner98R + dense coefficients, orbits/s (integrate phase)", arith=arith, N=N, ms=ms, value=N / ms * 1e3,
+             unit="orbits/s", accepted_per_orbit=float(cnt[1].mean()), tflops_alg=fl / ms / 1e9, frac_fp64_peak=fl / ms / 1e9 / peak_tf,
+             dense_store_gb=N * float(cnt[1].mean()) * 440 / 1e9)
+        xarr = torch.linspace(0.0, xf, G, dtype=torch.float64).cuda()
+        xarr[-1] = xf
+        for layout in (0, 1):
+            yarr = torch.empty((N, G, 6) if layout == 0 else (6, G, N), dtype=torch.float64, device="cuda")
+            best = 1e30
+            for _ in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st, _, ist = erk.InterpolateBatch(xarr, N, SaveInterpCoeffs=True, layout=layout, out=yarr)
+                e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            gb = N * G * 6 * 8 / 1e9
+            emit(config=4, what="Interpolate onto %d-point grid, layout %d" % (G, layout), arith=arith, N=N, ms=best, yarr_gb=gb,
+                 gbs_written=gb / best * 1e3, frac_hbm_peak=gb / best * 1e3 / HBM_GBS, points_per_s=N * G / best * 1e3, ok=bool((ist == 0).all()))
+            del yarr
+        del erk
+
+if "wp" in which:          # config 5: work-precision sweep, spatial CR3BP halo and two-body, all four methods
+    N = 1 << (12 if small else 16)
+    for sysname in ("halo", "twobody"):
+        for method, mname in ((F.ERK_DOP54, "DOP54"), (F.ERK_DOP853, "DOP853"), (F.ERK_VERNER65E, "Verner65E"), (F.ERK_VERNER98R, "Verner98R")):
+            row = {}
+            for i in range(6, 15, 2):
+                rtol = P.wp_rtol(i)
+                if sysname == "halo":
+                    sys_ = F.DiffEqSys(F.FLINT_SYS_CR3BP_SPATIAL, F.FLINT_EVSET_NONE, [P.HALO_MU])
+                    y0h, xf, atol, sid = P.perturbed_ensemble(P.HALO_Y0, N), P.HALO_PERIOD, 1e-80, F.FLINT_SYS_CR3BP_SPATIAL
+                else:
+                    sys_ = F.DiffEqSys(F.FLINT_SYS_TWOBODY, F.FLINT_EVSET_NONE, [P.TBP_GM])
+                    y0h, xf, atol, sid = P.perturbed_ensemble(P.TBP_Y0, N), P.tbp_period() * 10, rtol * 1e-3, F.FLINT_SYS_TWOBODY
+                erk = F.ERK()
+                assert erk.Init(sys_, 99000, Method=method, ATol=[atol], RTol=[rtol], Arith=0) == 0
+                ms, r = run(erk, 0.0, torch.from_numpy(y0h).cuda(), xf, StiffTest=1)
+                cnt = r["counters"].cpu().numpy().astype(np.int64)
+                fl = P.algorithmic_flops(method, sid, 6, cnt[0].sum(), cnt[1].sum())
+                row["1e-%d" % i] = dict(ms=round(ms, 3), traj_per_s=round(N / ms * 1e3), fcalls=float(cnt[3].mean()),
+                                        frac_fp64_peak=round(fl / ms / 1e9 / peak_tf, 4))
+            emit(config=5, system=sysname, method=mname, N=N, arith="strict", sweep=row)
