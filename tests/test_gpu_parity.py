@@ -176,6 +176,37 @@ def test_dense_output_and_interpolate(method, arith):
     assert st == F.FLINT_ERROR_INTP_OFF
 
 
+def test_interpolate_mappings_chunks_and_dense_grids():
+    """Both interpolation kernels (warp per trajectory for [N][G][nI] and small ensembles, thread per trajectory for
+    [nI][G][N] with N >= 4096), grids split into chunks (few trajectories, many points), non-uniform grids, and a grid
+    much finer / much coarser than the steps (several steps between two points near the lunar fly-by)."""
+    case = K.cr3bp_case(F.ERK_DOP853, 1e-9, 1, norb=1.0, interp_on=True)
+    N = 4096
+    y0 = P.cr3bp_ensemble(N, start=50)
+    rng = np.random.default_rng(7)
+    xarr = np.sort(np.concatenate([[0.0, case.xf], rng.uniform(0.0, case.xf, 60), np.linspace(case.xf * 0.49, case.xf * 0.51, 40)]))
+    g = case.run_gpu(y0)
+    o = case.run_oracle(y0, xarr=xarr)
+    K.compare_batch(g, o, case, "dense 4096")
+    for layout in (0, 1):
+        st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True, layout=layout)
+        assert st == 0
+        ya = yarr if layout == 0 else np.transpose(yarr, (2, 1, 0))
+        okt = ist == 0
+        assert okt.mean() > 0.99
+        K.assert_bit_equal(ya[okt], o["yarr"][okt], "Yarr 4096 layout %d" % layout)
+    for G in (5, 7001):                      # coarser than any step; many chunks of a fine grid
+        case = K.cr3bp_case(F.ERK_VERNER65E, 1e-8, 0, norb=1.0, interp_on=True, interp_states=[2, 5, 1], eventset=F.FLINT_EVSET_NONE)
+        y0 = P.cr3bp_ensemble(5, start=900)
+        xarr = np.linspace(0.0, case.xf, G)
+        xarr[-1] = case.xf
+        g, o = case.run_gpu(y0), case.run_oracle(y0, xarr=xarr)
+        for layout in (0, 1):
+            st, yarr, ist = g["erk"].InterpolateBatch(xarr, 5, SaveInterpCoeffs=True, layout=layout)
+            assert st == 0 and (ist == 0).all()
+            K.assert_bit_equal(yarr if layout == 0 else np.transpose(yarr, (2, 1, 0)), o["yarr"], "Yarr G=%d layout %d" % (G, layout))
+
+
 def test_interp_states_subset():
     case = K.halo_case(F.ERK_DOP853, 1e-9, 0, interp_on=True, interp_states=[1, 3, 5])
     y0 = P.perturbed_ensemble(P.HALO_Y0, 64)
