@@ -55,14 +55,15 @@ struct Workspace {                     /* trajectory state block + work lists of
 struct DenseStore {                    /* device-resident Xint / Bip of the last Integrate with InterpOn */
     int device = -1;
     long N = 0, cap = 0;
-    int nI = 0, pstar = 0;
-    double* dxint = nullptr; double* dbip = nullptr; int* dcount = nullptr;
+    int nI = 0, pstar = 0, rstride = 0;
+    double* dxint = nullptr; double* dbip = nullptr; int* dcount = nullptr; unsigned char* dflag = nullptr;
     void release()
     {
         if (dxint) cudaFree(dxint);
         if (dbip) cudaFree(dbip);
         if (dcount) cudaFree(dcount);
-        dxint = dbip = nullptr; dcount = nullptr; N = cap = 0;
+        if (dflag) cudaFree(dflag);
+        dxint = dbip = nullptr; dcount = nullptr; dflag = nullptr; N = cap = 0;
     }
 };
 
@@ -309,7 +310,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
 
     if (!cuda_ok(cudaSetDevice(ex.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const bool dense = me->interp_on;
-    const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, events_on, dense);
+    const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, events_on);
     if (!ke) {
         char buf[160];
         snprintf(buf, sizeof buf, "no kernel compiled for method=%d system=%d arith=%d events=%d dense=%d", me->method,
@@ -381,17 +382,21 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         long cap = ex.dense_cap > 0 ? ex.dense_cap : me->max_steps;
         if (cap > me->max_steps) cap = me->max_steps;
         DenseStore& D = me->dense;
-        if (D.device != ex.device || D.N != N || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || !D.dxint) {
+        /* a step slot holds the step's coefficients, (pstar+1)*nI doubles, and before that its log, 2n+2 doubles */
+        int rstride = me->nI * (me->pstar + 1);
+        if (rstride < 2 * n + 2) rstride = 2 * n + 2;
+        rstride += rstride & 1;
+        if (D.device != ex.device || D.N != N || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || D.rstride != rstride || !D.dxint) {
             D.release();
-            const size_t nb = szN * (size_t)cap * (size_t)me->nI * (size_t)(me->pstar + 1);
+            const size_t nb = szN * (size_t)cap * (size_t)rstride;
             if (cudaMalloc(&D.dxint, szN * (size_t)(cap + 1) * 8) != cudaSuccess || cudaMalloc(&D.dbip, nb * 8) != cudaSuccess ||
-                cudaMalloc(&D.dcount, szN * 4) != cudaSuccess) {
+                cudaMalloc(&D.dcount, szN * 4) != cudaSuccess || cudaMalloc(&D.dflag, szN * (size_t)cap) != cudaSuccess) {
                 cudaGetLastError(); D.release();
                 return me->status = fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; set flint_exec.dense_cap");
             }
-            D.device = ex.device; D.N = N; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar;
+            D.device = ex.device; D.N = N; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar; D.rstride = rstride;
         }
-        a.dense_cap = cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dense_count = D.dcount;
+        a.dense_cap = cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dense_count = D.dcount; a.dense_rstride = rstride; a.dflag = D.dflag;
         me->dense_is_scalar = scalar_call;
     }
     /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
@@ -500,6 +505,10 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             }
             cur = oth;
         }
+    }
+    if (le == cudaSuccess && dense) {                      /* coefficients of the logged steps (erk_kernel.cuh: erk_dense_kernel) */
+        le = ke->dense_coeffs(a, grid_all, 128, s);
+        g_launches += 1;
     }
     if (timed) cudaEventRecord(e1, s);
     if (!cuda_ok(le, "kernel launch")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
@@ -615,7 +624,7 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     int up = 1, down = 1;
     for (long i = 0; i + 1 < G; ++i) { if (!(xh[i] < xh[i + 1])) up = 0; if (!(xh[i] > xh[i + 1])) down = 0; }
     flint::InterpArgs a{};
-    a.N = N; a.G = G; a.nI = D.nI; a.pstar = D.pstar; a.cap = D.cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dcount = D.dcount;
+    a.N = N; a.G = G; a.nI = D.nI; a.pstar = D.pstar; a.cap = D.cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dcount = D.dcount; a.rstride = D.rstride;
     a.layout = layout; a.fma = me->arith == FLINT_ARITH_FMA;
     const size_t ny = (size_t)N * (size_t)G * (size_t)D.nI;
     double* d_y = nullptr; int* d_st = nullptr;

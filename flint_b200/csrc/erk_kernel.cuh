@@ -343,11 +343,64 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
     for (int i = 0; i < M; ++i) c.EV1[i] = EV1[i][0];                   /* what `EV0 = EV1` (:550) carries to the next step */
 }
 
+/* ---- dense-output storage (InterpOn), one contiguous run per trajectory (interp_kernel.cu):
+ *   dxint[N][cap+1]  Xint;   dbip[N][cap][rstride]  per accepted step Bip(ii,j) as [j][ii], (pstar+1)*nI doubles;
+ *   dflag[N][cap]    1 = the slot holds the step's LOG (X, h, Y, F0) and erk_dense_kernel still has to turn it into
+ *                    coefficients, 0 = coefficients.
+ * The hot loop only logs an accepted step (2n+2 doubles); the extra dense stages and the coefficients are computed
+ * afterwards by erk_dense_kernel, one thread per (trajectory, step), by recomputing the step from its log -- the same
+ * bits, because F is pure and the arithmetic is the same straight-line code.  Measured before the split (dense stages,
+ * coefficients and the 54-double store inside the lane loop): Verner98R 5.2x, DOP853 2.7x slower than without InterpOn. ---- */
+template <class METHOD, class SYS>
+__device__ __forceinline__ void store_dense_record(const KArgs& p, long idx, int acc, const double (&B)[METHOD::PSTAR + 1][SYS::N])
+{
+    constexpr int N = SYS::N, PS = METHOD::PSTAR;
+    double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)p.dense_rstride;
+    if (p.nI == N) {                   /* all states, in order (the default): the record is B itself */
+        if (((PS + 1) * N) % 2 == 0) {
+#pragma unroll
+            for (int q = 0; q < (PS + 1) * N / 2; ++q)
+                reinterpret_cast<double2*>(rec)[q] = make_double2(B[(2 * q) / N][(2 * q) % N], B[(2 * q + 1) / N][(2 * q + 1) % N]);
+        } else {
+#pragma unroll
+            for (int j = 0; j <= PS; ++j)
+#pragma unroll
+                for (int c = 0; c < N; ++c) rec[j * N + c] = B[j][c];
+        }
+    } else {
+        for (int j = 0; j <= PS; ++j)
+            for (int ii = 0; ii < p.nI; ++ii) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
+                rec[j * p.nI + ii] = v;
+            }
+    }
+    p.dflag[idx * p.dense_cap + (acc - 1)] = 0;
+}
+template <class SYS>
+__device__ __forceinline__ void log_dense_step(const KArgs& p, long idx, int acc, double X, double h, const double (&Y)[SYS::N], const double (&F0)[SYS::N])
+{
+    constexpr int N = SYS::N;
+    if (acc > p.dense_cap) return;
+    p.dxint[idx * (p.dense_cap + 1) + acc] = X + h;
+    double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)p.dense_rstride;    /* rstride is even: 16-byte aligned */
+    reinterpret_cast<double2*>(rec)[0] = make_double2(X, h);
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) reinterpret_cast<double2*>(rec)[1 + q] = make_double2(Y[2 * q], Y[2 * q + 1]);
+    if (N % 2) rec[2 + N - 1] = Y[N - 1];
+#pragma unroll
+    for (int c = 0; c < N; ++c) rec[2 + N + c] = F0[c];
+    p.dflag[idx * p.dense_cap + (acc - 1)] = 1;
+}
+
 /* ---- the tail of an accepted step (:555-635): dense store, stale-action quirk, natural-step output,
  * advance, new step size, too-small test.  Shared by the hot path (state in registers) and by the
  * deferred event commit (state in the local-memory context). ---- */
-template <class METHOD, class SYS, bool FMA, bool EVENTS, bool DENSE>
-__device__ __forceinline__ void commit_tail(const KArgs& p, long idx, bool eventsOn, int evAction, double hSign, double hmax,
+/* dense_mode (InterpOn only): 1 = store the step's dense coefficients B now (steps committed by the event code),
+ * 2 = the step was logged for erk_dense_kernel (hot path), 0 = InterpOn is off. */
+template <class METHOD, class SYS, bool FMA, bool EVENTS>
+__device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_mode, bool eventsOn, int evAction, double hSign, double hmax,
         double& X, double (&Y)[SYS::N], double (&F0)[SYS::N], double& h_io, double& hbyhoptOld, bool& lastRej, bool LAST, int& st,
         int& fcalls, int acc, double h, double (&Y1)[SYS::N], const double (&F0new)[SYS::N], double Err, double hbyhopt,
         bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N])
@@ -355,31 +408,11 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, bool event
     constexpr int N = SYS::N, PS = METHOD::PSTAR;
     const long NN = p.N;
     const bool const_step = p.const_step != 0;
-    if constexpr (DENSE) {                                              /* :555-566 */
+    if (dense_mode != 0) {                                              /* :555-566 */
         if (!bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }
-        if (acc <= p.dense_cap) {          /* per-trajectory runs: dxint[N][cap+1], dbip[N][cap][pstar+1][nI] (interp_kernel.cu) */
+        if (dense_mode == 1 && acc <= p.dense_cap) {   /* per-trajectory runs: dxint[N][cap+1], dbip[N][cap][rstride] (interp_kernel.cu) */
             p.dxint[idx * (p.dense_cap + 1) + acc] = X + h;
-            double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)((PS + 1) * p.nI);
-            if (p.nI == N) {               /* all states, in order (the default): the record is B itself */
-                if (((PS + 1) * N) % 2 == 0) {
-#pragma unroll
-                    for (int q = 0; q < (PS + 1) * N / 2; ++q)
-                        reinterpret_cast<double2*>(rec)[q] = make_double2(B[(2 * q) / N][(2 * q) % N], B[(2 * q + 1) / N][(2 * q + 1) % N]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j <= PS; ++j)
-#pragma unroll
-                        for (int c = 0; c < N; ++c) rec[j * N + c] = B[j][c];
-                }
-            } else {
-                for (int j = 0; j <= PS; ++j)
-                    for (int ii = 0; ii < p.nI; ++ii) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
-                        rec[j * p.nI + ii] = v;
-                    }
-            }
+            store_dense_record<METHOD, SYS>(p, idx, acc, B);
         }
     }
     if (EVENTS && eventsOn) {                                           /* :572-582 (quirks Q4, Q5) */
@@ -416,19 +449,20 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, bool event
 /* ---- deferred commit of a step with events to locate.  Called at the top of the lane loop, where only
  * the loop-carried state is live: the step's data was stashed in the context when the sign change was
  * seen, so nothing of the hot step has to survive the call.  Runs the rare path, then the commit tail. ---- */
-template <class METHOD, class SYS, bool FMA, bool DENSE>
+template <class METHOD, class SYS, bool FMA>
 __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& p, EvCtx<METHOD, SYS>& c, long idx, double hSign)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
     event_rare_path<METHOD, SYS, FMA>(sys, p, c, idx, hSign);
 #pragma unroll
     for (int i = 0; i < M; ++i) c.EV0[i] = c.EV1[i];                  /* :550 */
-    if constexpr (DENSE) {
+    const bool dense = p.dense_cap > 0;
+    if (dense) {
         if (c.h != c.h_stage) c.haveB = false;                         /* truncated: rebuild the dense stages (quirk Q6) */
         remat_bip<METHOD, SYS, FMA>(sys, p, c);
     }
     double Xn = c.X, hio = c.h;
-    commit_tail<METHOD, SYS, FMA, true, DENSE>(p, idx, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
+    commit_tail<METHOD, SYS, FMA, true>(p, idx, dense ? 1 : 0, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
                                                c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B);
     c.X = Xn; c.h = hio;       /* new X, next step size; new Y in c.Y, new F0 in c.F0old */
     (void)PS;
@@ -514,7 +548,7 @@ __device__ __forceinline__ int state_load(const KArgs& p, long idx, Lane<SYS>& L
 }
 
 /* final status resolution and result store (:642-708) */
-template <class SYS, bool DENSE>
+template <class SYS>
 __device__ __forceinline__ void store_results(const KArgs& p, long idx, const Lane<SYS>& L)
 {
     constexpr int N = SYS::N;
@@ -539,7 +573,7 @@ __device__ __forceinline__ void store_results(const KArgs& p, long idx, const La
     if (p.stifftest) p.stifftest[idx] = L.stiffOut;
     if (p.ev_count) p.ev_count[idx] = L.evCount;
     if (p.steps_count) p.steps_count[idx] = L.acc + 1;
-    if (DENSE && p.dense_count) p.dense_count[idx] = L.acc;
+    if (p.dense_count) p.dense_count[idx] = L.acc;
     p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
 }
 template <class SYS> __host__ __device__ constexpr bool is_plane_variant()
@@ -555,7 +589,7 @@ __device__ __forceinline__ bool keeps_going(const KArgs& p, const Lane<SYS>& L)
 }
 
 /* ===================================================================== init: one thread per trajectory (:204-259) */
-template <class METHOD, class SYS, bool FMA, bool DENSE>
+template <class METHOD, class SYS, bool FMA>
 __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX;
@@ -640,14 +674,14 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
 #pragma unroll
         for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + 0) * NN + idx] = L.Y[c];
     }
-    if (DENSE && p.dense_cap > 0) p.dxint[idx * (p.dense_cap + 1)] = L.X;   /* :259 */
-    if (!keeps_going<SYS>(p, L)) store_results<SYS, DENSE>(p, idx, L);
+    if (p.dense_cap > 0) p.dxint[idx * (p.dense_cap + 1)] = L.X;            /* :259 */
+    if (!keeps_going<SYS>(p, L)) store_results<SYS>(p, idx, L);
     else state_store<SYS>(p, idx, L, 0);
 }
 
 /* ===================================================================== the hot loop */
 /* EVMODE 0: no events.  1: events located inside the lane loop.  2: steps with events to locate are parked. */
-template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
+template <class METHOD, class SYS, bool FMA, int EVMODE>
 __global__ void __launch_bounds__(FLINT_BLOCK_THREADS, FLINT_MIN_BLOCKS)
 erk_step_kernel(const __grid_constant__ KArgs p)
 {
@@ -706,7 +740,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
         if (EVMODE == 1 && pending) {
-            deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, L.hSign);
+            deferred_event_commit<METHOD, SYS, FMA>(sys, p, ctx, idx, L.hSign);
             L.X = ctx.X; L.h = ctx.h; L.hbyhoptOld = ctx.hbyhoptOld; L.lastRej = ctx.lastRej; L.LAST = ctx.LAST; L.st = ctx.st;
             L.fcalls = ctx.fcalls; L.evmask = ctx.evmask; L.evAction = ctx.action; L.evCount = ctx.evcount;
 #pragma unroll
@@ -714,7 +748,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 #pragma unroll
             for (int i = 0; i < M; ++i) { L.EV0[i] = ctx.EV0[i]; L.EvDir[i] = ctx.EvDir[i]; }
             pending = false;
-            if (!keeps_going<SYS>(p, L)) { store_results<SYS, DENSE>(p, idx, L); have = false; }
+            if (!keeps_going<SYS>(p, L)) { store_results<SYS>(p, idx, L); have = false; }
         }
 
         /* ---------------- one step attempt for every lane that owns a trajectory (:263-637) ---------------- */
@@ -722,7 +756,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             if (L.hSign * (madd<FMA>(fac, L.h, L.X) - L.Xf) > 0.0) { L.h = L.Xf - L.X; L.LAST = true; }   /* :268-271 */
             const double h = L.h;
             double Ynew[N], Ypre[N], Err;
-            METHOD::template step<SYS, FMA, DENSE>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
+            METHOD::template step<SYS, FMA, false>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
             L.total += 1;
             double hbyhopt = 1.0;
             if (!const_step) hbyhopt = flint_det_pow(Err, expo);            /* src/StepSz.f90:153 */
@@ -808,13 +842,23 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                     }
                 }
                 if (!rare) {
-                    double B[PS + 1][N];       /* dead unless DENSE */
-                    if constexpr (DENSE) METHOD::template dense_coeffs<SYS, FMA>(ks, L.Y, h, Ynew, B, p.coef);
+                    double B[PS + 1][N];       /* unused when the step is logged for erk_dense_kernel */
+                    const bool dense = p.dense_cap > 0;
+                    int dense_mode = 0;
+                    if (dense) {
+                        if constexpr (METHOD::FC_DENSE == 0) {      /* no extra stages (DOP54): the coefficients are cheaper than a recomputation */
+                            METHOD::template dense_coeffs<SYS, FMA>(ks, L.Y, h, Ynew, B, p.coef);
+                            dense_mode = 1;
+                        } else {
+                            log_dense_step<SYS>(p, idx, L.acc, L.X, h, L.Y, L.F0);
+                            dense_mode = 2;
+                        }
+                    }
                     double hio = h, F0new[N];
                     ks.template load<METHOD::SLOT_F0NEW>(F0new);
-                    commit_tail<METHOD, SYS, FMA, EVENTS, DENSE>(p, idx, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
-                                                                 L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, F0new, Err, hbyhopt,
-                                                                 bip_counted, Ynew, B);
+                    commit_tail<METHOD, SYS, FMA, EVENTS>(p, idx, dense_mode, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
+                                                          L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, F0new, Err, hbyhopt,
+                                                          bip_counted, Ynew, B);
                     L.h = hio;
                 }
             } else {                                                        /* :607-624 */
@@ -825,13 +869,13 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 L.LAST = false;
                 if (!const_step && fabs(L.h) * 0.01 <= fabs(L.X) * kEps) L.st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
             }
-            if (!pending && !parked && !keeps_going<SYS>(p, L)) { store_results<SYS, DENSE>(p, idx, L); have = false; }
+            if (!pending && !parked && !keeps_going<SYS>(p, L)) { store_results<SYS>(p, idx, L); have = false; }
         }
     }
 }
 
 /* ===================================================================== parked trajectories: locate + commit */
-template <class METHOD, class SYS, bool FMA, bool DENSE>
+template <class METHOD, class SYS, bool FMA>
 __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX;
@@ -864,46 +908,83 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
     ctx.evcount = L.evCount; ctx.LAST = L.LAST; ctx.bip_counted = (flags & kFlagBipCounted) != 0; ctx.haveB = false;
     ctx.Err = d[D::ERR * c]; ctx.hbyhopt = d[D::HBH * c]; ctx.hbyhoptOld = L.hbyhoptOld; ctx.hmax = L.hmax; ctx.acc = L.acc;
     ctx.lastRej = L.lastRej;
-    deferred_event_commit<METHOD, SYS, FMA, DENSE>(sys, p, ctx, idx, L.hSign);
+    deferred_event_commit<METHOD, SYS, FMA>(sys, p, ctx, idx, L.hSign);
     L.X = ctx.X; L.h = ctx.h; L.hbyhoptOld = ctx.hbyhoptOld; L.lastRej = ctx.lastRej; L.LAST = ctx.LAST; L.st = ctx.st;
     L.fcalls = ctx.fcalls; L.evmask = ctx.evmask; L.evAction = ctx.action; L.evCount = ctx.evcount;
 #pragma unroll
     for (int i = 0; i < N; ++i) { L.Y[i] = ctx.Y[i]; L.F0[i] = ctx.F0old[i]; }
 #pragma unroll
     for (int i = 0; i < M; ++i) { L.EV0[i] = ctx.EV0[i]; L.EvDir[i] = ctx.EvDir[i]; }
-    if (!keeps_going<SYS>(p, L)) store_results<SYS, DENSE>(p, idx, L);     /* the next pass skips it (done flag) */
+    if (!keeps_going<SYS>(p, L)) store_results<SYS>(p, idx, L);     /* the next pass skips it (done flag) */
     else state_store<SYS>(p, idx, L, 0);
 }
 
+/* ===================================================================== dense output: coefficients from the step logs */
+template <class METHOD, class SYS, bool FMA>
+__global__ void __launch_bounds__(128) erk_dense_kernel(const __grid_constant__ KArgs p)
+{
+    constexpr int N = SYS::N, PS = METHOD::PSTAR;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.N) return;
+    int nacc = p.dense_count[t];
+    if (nacc > p.dense_cap) nacc = (int)p.dense_cap;
+    SYS sys;
+    sys.load(p.sp);
+    for (int s = blockIdx.y; s < nacc; s += gridDim.y) {
+        if (p.dflag[t * p.dense_cap + s] == 0) continue;             /* written by the event code */
+        const double* __restrict__ rec = p.dbip + (t * p.dense_cap + s) * (long)p.dense_rstride;
+        const double X = rec[0], h = rec[1];
+        double Y[N], F0[N], Yn[N], Yp[N], e, B[PS + 1][N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) { Y[c] = rec[2 + c]; F0[c] = rec[2 + N + c]; }
+        KStore<METHOD, SYS, 0u> ks;
+        ks.s = nullptr;
+        METHOD::template step<SYS, FMA, true>(sys, X, Y, F0, h, h, ks, Yn, Yp, p.tol, false, e, p.coef);
+        METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Yn, B, p.coef);
+        store_dense_record<METHOD, SYS>(p, t, s + 1, B);
+    }
+}
+
 /* Host-side launchers shared by all instantiations (inst_*.cu). */
-template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
+template <class METHOD, class SYS, bool FMA, int EVMODE>
 cudaError_t launch_step(const KArgs& a, int grid, int block, cudaStream_t s)
 {
     constexpr int smem = kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>();
     if (smem > 0 && block != FLINT_BLOCK_THREADS) return cudaErrorInvalidConfiguration;   /* the shared-memory layout is compiled for this block size */
     if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE><<<grid, block, smem, s>>>(a);
+    erk_step_kernel<METHOD, SYS, FMA, EVMODE><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
-template <class METHOD, class SYS, bool FMA, bool DENSE>
+template <class METHOD, class SYS, bool FMA>
 cudaError_t launch_init(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    erk_init_kernel<METHOD, SYS, FMA, DENSE><<<grid, block, 0, s>>>(a);
+    erk_init_kernel<METHOD, SYS, FMA><<<grid, block, 0, s>>>(a);
     return cudaGetLastError();
 }
-template <class METHOD, class SYS, bool FMA, bool DENSE>
+template <class METHOD, class SYS, bool FMA>
 cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    erk_event_kernel<METHOD, SYS, FMA, DENSE><<<grid, block, 0, s>>>(a);
+    erk_event_kernel<METHOD, SYS, FMA><<<grid, block, 0, s>>>(a);
     return cudaGetLastError();
 }
-template <class METHOD, class SYS, bool FMA, int EVMODE, bool DENSE>
+/* grid = (ceil(N / block), steps handled in parallel per trajectory) */
+template <class METHOD, class SYS, bool FMA>
+cudaError_t launch_dense(const KArgs& a, int grid, int block, cudaStream_t s)
+{
+    long gy = 4L * 148 * 16 * 32 / (a.N > 0 ? a.N : 1);              /* ~4 waves of threads over the device */
+    if (gy < 1) gy = 1;
+    if (gy > a.dense_cap) gy = a.dense_cap;
+    if (gy > 4096) gy = 4096;
+    erk_dense_kernel<METHOD, SYS, FMA><<<dim3((unsigned)grid, (unsigned)gy), block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <class METHOD, class SYS, bool FMA, int EVMODE>
 cudaError_t occupancy_step(int* blocks_per_sm, int block)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE, DENSE>, block,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block,
                                                          kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>());
 }
 template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }

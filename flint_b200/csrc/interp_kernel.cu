@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     if (a.status[t] != FLINT_SUCCESS) return;
     const int acc = a.dcount[t];
     const double* __restrict__ xi = a.dxint + t * (a.cap + 1);
-    const double* __restrict__ rec0 = a.dbip + t * a.cap * (long)RS;
+    const double* __restrict__ rec0 = a.dbip + t * a.cap * (long)a.rstride;
     const double hs = sign1(xi[acc] - xi[0]);
     /* chunk start: smallest j in [1,acc] (1-based) with hs*(Xint(j+1) - x) >= 0 */
     int loc;
@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     }
     double B[PS + 1][NI];
     double X0 = xi[loc - 1], X1, h;
-    RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * RS, xi + loc);
+    RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * a.rstride, xi + loc);
     RecBuf<RS>::take(rb, &B[0][0], X1);                               /* step loc: coefficients and Xint(loc+1) */
     h = X1 - X0;
-    if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * RS, xi + loc + 1);
+    if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * a.rstride, xi + loc + 1);
     for (long g = g0; g < g1; ++g) {
         const double x = xs[g - g0];
         if (loc < acc && hs * (X1 - x) < 0.0) {                       /* forward cursor (:85-103) */
@@ -131,11 +131,11 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
             RecBuf<RS>::take(rb, &B[0][0], X1);                       /* the record that was on its way */
             if (loc < acc && hs * (X1 - x) < 0.0) {                   /* several steps between two grid points: walk Xint */
                 do { loc += 1; X0 = X1; X1 = xi[loc]; } while (loc < acc && hs * (X1 - x) < 0.0);
-                RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * RS, xi + loc);
+                RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * a.rstride, xi + loc);
                 RecBuf<RS>::take(rb, &B[0][0], X1);
             }
             h = X1 - X0;
-            if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * RS, xi + loc + 1);
+            if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * a.rstride, xi + loc + 1);
         }
         const double theta = (x - X0) / h;
         double tk[PS + 1];
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
     if (active) {
         acc = a.dcount[t];
         xi = a.dxint + t * (a.cap + 1);
-        rec0 = a.dbip + t * a.cap * (long)RS;
+        rec0 = a.dbip + t * a.cap * (long)a.rstride;
         hs = sign1(xi[acc] - xi[0]);
         const double x = a.xarr[g0];                                   /* chunk start: smallest j in [1,acc] with hs*(Xint(j+1) - x) >= 0 */
         int lo = 1, hi = acc;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
                 if (want_hi > acc + 1) want_hi = acc + 1;
                 __syncwarp();                                          /* nobody still reads the slots about to be overwritten */
                 for (int sidx = ring_hi; sidx < want_hi; ++sidx) {
-                    const double* __restrict__ r = rec0 + (long)(sidx - 1) * RS;
+                    const double* __restrict__ r = rec0 + (long)(sidx - 1) * a.rstride;
                     double* d = s_ring[warp][sidx % kRing];
                     if (RS % 2 == 0) {
                         if (lane < RS / 2) {

@@ -77,6 +77,7 @@ struct KArgs {
     long ev_cap; int* ev_count; double* ev_rec;          /* [(n+2)][cap][N] */
     int steps_on; long steps_cap; double* xint; double* yint; int* steps_count;   /* IntStepsOn output */
     long dense_cap; double* dxint; double* dbip; int* dense_count; int nI; int istates[FLINT_MAX_N];   /* InterpOn storage */
+    int dense_rstride; unsigned char* dflag;     /* doubles per step slot (>= (pstar+1)*nI and >= 2n+2, even); slot holds a log (1) or coefficients (0) */
     /* trajectory state block + work lists (erk_kernel.cuh) */
     double* sd; int* si; long scap;              /* [fields][scap] */
     const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */
@@ -92,6 +93,7 @@ struct InterpArgs {
     int nI, pstar;
     long cap;
     const double* dxint; const double* dbip; const int* dcount;
+    int rstride;                     /* doubles per step slot in dbip */
     const double* xarr;
     double* yarr; int layout;        /* 0: [N][G][nI], 1: [nI][G][N] */
     int* status;                     /* [N] */
@@ -105,18 +107,19 @@ typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t
 typedef cudaError_t (*occupancy_fn)(int* blocks_per_sm, int block);
 struct KernelEntry {
     int method, system;
-    bool fma, events, dense;
+    bool fma, events;
     launch_fn init;              /* erk_init_kernel */
     launch_fn step;              /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
     launch_fn step_park;         /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
     launch_fn event;             /* erk_event_kernel (NULL when events == false) */
+    launch_fn dense_coeffs;      /* erk_dense_kernel: dense-output coefficients from the step logs */
     launch_fn step_plane;        /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
     occupancy_fn occupancy, occupancy_park;
     void (*load_coefficients)(double* dst);
     int n_state_doubles, n_state_ints;
 };
 void register_kernel(const KernelEntry&);
-const KernelEntry* find_kernel(int method, int system, bool fma, bool events, bool dense);
+const KernelEntry* find_kernel(int method, int system, bool fma, bool events);
 int kernel_count();
 
 }  // namespace flint

@@ -10,10 +10,10 @@ static std::vector<KernelEntry>& table()
     return t;
 }
 void register_kernel(const KernelEntry& e) { table().push_back(e); }
-const KernelEntry* find_kernel(int method, int system, bool fma, bool events, bool dense)
+const KernelEntry* find_kernel(int method, int system, bool fma, bool events)
 {
     for (const KernelEntry& e : table())
-        if (e.method == method && e.system == system && e.fma == fma && e.events == events && e.dense == dense) return &e;
+        if (e.method == method && e.system == system && e.fma == fma && e.events == events) return &e;
     return nullptr;
 }
 int kernel_count() { return (int)table().size(); }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 16 and "flint_erk_integrate_batch" in syms
     for s in syms:
         assert hasattr(lib, s), "libflint_b200.so does not export %s" % s
-    assert lib.flint_b200_kernel_count() == 96      # 4 methods x (2 systems x 8 + 2 systems x 4) variants
+    assert lib.flint_b200_kernel_count() == 48      # 4 methods x (2 systems x 4 + 2 systems x 2) (arithmetic, events) entries
 
 
 def test_enum_values_are_the_references():
