@@ -44,7 +44,7 @@ if "lorenz" in which:      # config 2: Lorenz, 2^20 perturbed ICs, DOP54, rtol 1
              ok=float((r["status"] == 0).float().mean()))
 
 if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolation onto a shared uniform grid
-    N = 1 << (14 if small else 17)
+    N = 1 << (14 if small else 17)      # 2^17: Yarr (62.9 GB) + dense store (37 GB) fit one GPU; BASELINE's 2^18 needs two passes or two GPUs
     G = 10000
     for arith in (0, 1):
         sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
@@ -70,7 +70,8 @@ if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolat
             emit(config=4, what="Interpolate onto %d-point grid, layout %d" % (G, layout), arith=arith, N=N, ms=best, yarr_gb=gb,
                  gbs_written=gb / best * 1e3, frac_hbm_peak=gb / best * 1e3 / HBM_GBS, points_per_s=N * G / best * 1e3, ok=bool((ist == 0).all()))
             del yarr
-        del erk
+        del erk, y0, xarr
+        import gc; gc.collect(); torch.cuda.empty_cache()
 
 if "wp" in which:          # config 5: work-precision sweep, spatial CR3BP halo and two-body, all four methods
     N = 1 << (12 if small else 16)
