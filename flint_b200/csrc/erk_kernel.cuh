@@ -403,7 +403,7 @@ template <class METHOD, class SYS, bool FMA, bool EVENTS>
 __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_mode, bool eventsOn, int evAction, double hSign, double hmax,
         double& X, double (&Y)[SYS::N], double (&F0)[SYS::N], double& h_io, double& hbyhoptOld, bool& lastRej, bool LAST, int& st,
         int& fcalls, int acc, double h, double (&Y1)[SYS::N], const double (&F0new)[SYS::N], double Err, double hbyhopt,
-        bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N])
+        bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N], double& powKey, double& powVal)
 {
     constexpr int N = SYS::N, PS = METHOD::PSTAR;
     const long NN = p.N;
@@ -435,7 +435,18 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_
     double hnew;
     if (!const_step) {                                                  /* :595-605, src/StepSz.f90:156-168 */
         const double SFl = p.szp[0], SFmin = p.szp[1], SFmax = p.szp[2], beta = p.szp[3];
-        if (beta != 0.0) hbyhopt = hbyhopt / flint_det_pow(hbyhoptOld, beta);
+        if (beta != 0.0) {
+            /* hbyhoptOld is a running maximum of the error norm: it changes a few times per trajectory, so its power
+             * is kept from step to step where the method's default controller uses it (DOP54: one pow per step saved) */
+            constexpr bool CACHE = METHOD::ID == ERK_DOP54;
+            double pw;
+            if (CACHE && hbyhoptOld == powKey) pw = powVal;
+            else {
+                pw = det_pow_dev(hbyhoptOld, beta);
+                if (CACHE) { powKey = hbyhoptOld; powVal = pw; }
+            }
+            hbyhopt = hbyhopt / pw;
+        }
         hnew = h * dmin(SFmax, dmax(SFmin, SFl / hbyhopt));
         hbyhoptOld = dmax(Err, hbyhoptOld);
         if (fabs(hnew) > hmax) hnew = hSign * hmax;
@@ -461,9 +472,9 @@ __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& 
         if (c.h != c.h_stage) c.haveB = false;                         /* truncated: rebuild the dense stages (quirk Q6) */
         remat_bip<METHOD, SYS, FMA>(sys, p, c);
     }
-    double Xn = c.X, hio = c.h;
+    double Xn = c.X, hio = c.h, pk = qnan(), pv = 0.0;
     commit_tail<METHOD, SYS, FMA, true>(p, idx, dense ? 1 : 0, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
-                                               c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B);
+                                               c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B, pk, pv);
     c.X = Xn; c.h = hio;       /* new X, next step size; new Y in c.Y, new F0 in c.F0old */
     (void)PS;
 }
@@ -665,7 +676,7 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
         const double dMax = dmax(d1, fabs(d2));
         double h1;
         if (dMax <= 1.0e-15) h1 = dmax(1.0e-6, fabs(h0) * 1.0e-3);
-        else h1 = flint_det_pow(0.01 / dMax, 1.0 / (double)METHOD::P);
+        else h1 = det_pow_dev(0.01 / dMax, 1.0 / (double)METHOD::P);
         L.h = L.hSign * dmin(dmin(100.0 * fabs(h0), h1), L.hmax);
         L.fcalls += 1;
     }
@@ -712,6 +723,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 #pragma unroll
     for (int i = 0; i < M; ++i) { L.EV0[i] = 0; L.EvDir[i] = 0; }
     EvCtx<METHOD, SYS> ctx;                 /* EVMODE 1 only: local memory, touched when an event has to be located */
+    double powKey = qnan(), powVal = 0.0;   /* pow(hbyhoptOld, beta) of this lane's trajectory (commit_tail) */
     extern __shared__ double flint_smem[];
     KStore<METHOD, SYS, METHOD::SMEM_SLOTS> ks;
     ks.s = flint_smem + threadIdx.x;
@@ -725,7 +737,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 const long i = p.list_in ? (long)p.list_in[k] : k;
                 if (i >= 0) {
                     const int flags = state_load<SYS>(p, i, L);
-                    if (!(flags & kFlagDone)) { idx = i; have = true; }
+                    if (!(flags & kFlagDone)) { idx = i; have = true; powKey = qnan(); }
                 }
             } else exhausted = true;
         }
@@ -759,7 +771,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             METHOD::template step<SYS, FMA, false>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
             L.total += 1;
             double hbyhopt = 1.0;
-            if (!const_step) hbyhopt = flint_det_pow(Err, expo);            /* src/StepSz.f90:153 */
+            if (!const_step) hbyhopt = det_pow_dev(Err, expo);            /* src/StepSz.f90:153 */
             bool parked = false;
             if (Err <= 1.0) {                                               /* :283 */
                 L.fcalls += METHOD::FC_ACC;
@@ -858,7 +870,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                     ks.template load<METHOD::SLOT_F0NEW>(F0new);
                     commit_tail<METHOD, SYS, FMA, EVENTS>(p, idx, dense_mode, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
                                                           L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, F0new, Err, hbyhopt,
-                                                          bip_counted, Ynew, B);
+                                                          bip_counted, Ynew, B, powKey, powVal);
                     L.h = hio;
                 }
             } else {                                                        /* :607-624 */

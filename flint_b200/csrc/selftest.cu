@@ -46,6 +46,12 @@ __global__ void selftest_kernel(long n, unsigned long long seed, unsigned long l
         if (ok1) { pass_div += 1; if (!same(q1, x / d)) bad += 1; }
         if (ok2) { pass_div += 1; if (!same(q2, x2 / d)) bad += 1; }
         if (ok3) { pass_sqrt += 1; if (!same(s, sqrt(fabs(x)))) bad += 1; }
+        {   /* the device pow of the step-size controller against det_pow.h: error norms 1e-30..1e4 and any pattern, exponents of the controllers */
+            const double px = (i % 5 == 0) ? fabs(x) : exp2(-100.0 + 114.0 * ((double)(mix(k + 7) >> 11) * (1.0 / 9007199254740992.0)));
+            const double ex[6] = {0.125, 1.0 / 6.0 - 0.04 * 0.75, 0.04, 0.2, 1.0 / 9.0, -0.3};
+            const double py = ex[i % 6];
+            if (!same(flint::det_pow_dev(px, py), flint_det_pow(px, py))) bad += 1;
+        }
     }
     atomicAdd(&out[0], bad); atomicAdd(&out[1], pass_div); atomicAdd(&out[2], pass_sqrt);
 }
