@@ -307,10 +307,11 @@ class ERK:
     def IntegrateBatch(self, X0, Y0, Xf, StepSz=None, UseConstStepSz=None, StepAdvance=None, IntStepsOn=None,
                        EventMask=None, EventStates=False, StiffTest=None, params=None, MaxEvents=4, StepsCap=None,
                        out=None, device=0, stream=None, dense_cap=0, block_threads=0, blocks_per_sm=0, want_counters=True,
-                       event_mode=0, plane_variant=0):
+                       event_mode=0, plane_variant=0, async_=False):
         """Y0: (n, N) structure-of-arrays, numpy (host buffers: the call stages H2D/D2H itself) or a
         torch CUDA tensor (device buffers: nothing is copied).  Xf scalar or (N,).  Returns a dict of
-        SoA outputs (numpy or torch, matching the input kind)."""
+        SoA outputs (numpy or torch, matching the input kind).  async_ (device buffers only): return after enqueueing
+        on the stream; the caller synchronises before reading the outputs."""
         n = self.sys.n
         keep = []
         io = self._int_opts(UseConstStepSz, StepAdvance, IntStepsOn, EventMask, params, keep)
@@ -366,8 +367,8 @@ class ERK:
             ecount = out.get("nEvents") if out.get("nEvents") is not None else zeros((N,), i32)
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
-        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, int(dense_cap), int(block_threads),
-                   int(blocks_per_sm), int(event_mode), int(plane_variant))
+        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, int(bool(async_) and on_dev), int(dense_cap),
+                   int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant))
         x0s = float(X0) if x0v is None else 0.0
         st = lib().flint_erk_integrate_batch(self._h, N, x0s, _ptr(x0v), _ptr(Y0), _ptr(xf), _ptr(yf), _ptr(h), C.byref(io),
                                              _ptr(counters), _ptr(status), C.byref(steps) if steps else None,

@@ -304,6 +304,23 @@ def test_device_resident_buffers_match_host_path():
         K.assert_bit_equal(d[key].cpu().numpy(), g[key], key)
 
 
+def test_async_schedule_matches_synchronous_call():
+    """flint_exec.async: no host read-back between passes -- a fixed schedule of step / event kernels (empty ones return at
+    once) that ends with an in-loop-event pass.  One event per orbit (one round), two (two rounds) and an event per
+    half period (more rounds than the schedule has: the last pass mops up) must equal the synchronous call and the oracle."""
+    import torch
+    cases = [(K.cr3bp_case(F.ERK_DOP853, 1e-11, 0), P.cr3bp_ensemble(700, start=31)),
+             (K.cr3bp_case(F.ERK_DOP54, 1e-9, 1, eventset=F.FLINT_EVSET_XY_CROSSING), P.cr3bp_ensemble(300, start=77)),
+             (K.twobody_case(F.ERK_VERNER98R, 1e-10, 0, nper=5, eventset=F.FLINT_EVSET_APSIS, max_events=16), P.perturbed_ensemble(P.TBP_Y0, 200)),
+             (K.lorenz_case(F.ERK_VERNER65E, 1e-9, 1, xf=5.0), P.lorenz_ensemble(300))]
+    for case, y0 in cases:
+        o = case.run_oracle(y0)
+        g = case.run_gpu(torch.from_numpy(y0).cuda(), async_=True)
+        torch.cuda.synchronize()
+        g = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in g.items()}
+        K.compare_batch(g, o, case, "async")
+
+
 def test_full_size_properties():
     """BASELINE size (2^20 orbits): size-independent properties -- every trajectory succeeds, reaches
     Xf exactly, locates exactly one event of id 2 on the y-axis crossing, Jacobi drift stays at the
