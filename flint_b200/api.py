@@ -22,6 +22,7 @@ import numpy as np
 
 # ---- enums (values are ABI; src/FLINT_base.f90:43-61,86-120; src/ERK.f90:56-66) ----
 FLINT_SUCCESS, FLINT_EVENT_TERM, FLINT_STIFF_PROBLEM, FLINT_ERROR, FLINT_ERROR_PARAMS = 0, 1, 2, 3, 4
+FLINT_SYS_USER_BASE = 100
 FLINT_ERROR_MAXSTEPS, FLINT_ERROR_MEMALLOC, FLINT_ERROR_MEMDEALLOC, FLINT_ERROR_DIMENSION = 5, 6, 7, 8
 FLINT_ERROR_STEPSZ_TOOSMALL, FLINT_ERROR_INTPSTATES, FLINT_ERROR_INTP_ARRAY, FLINT_ERROR_INTP_OFF = 9, 10, 11, 12
 FLINT_ERROR_INIT_REQD, FLINT_ERROR_EVENTPARAMS, FLINT_ERROR_EVENTROOT, FLINT_ERROR_CONSTSTEPSZ = 13, 14, 15, 16
@@ -145,10 +146,11 @@ class DiffEqSys:
     """`type, extends(DiffEqSys)` of the reference (src/FLINT_base.f90:220-227): n, m, F, G.
     F and G are device functors compiled into the library, selected by id."""
 
-    def __init__(self, system_id, eventset_id=FLINT_EVSET_NONE, sysparams=()):
+    def __init__(self, system_id, eventset_id=FLINT_EVSET_NONE, sysparams=(), n=None, m=None):
+        """n, m: only for user systems (ids >= FLINT_SYS_USER_BASE), whose sizes the library checks against the functor."""
         self.system_id, self.eventset_id = system_id, eventset_id
-        self.n = _SYS_N[system_id]
-        self.m = _EVSET_M[eventset_id]
+        self.n = _SYS_N[system_id] if n is None else int(n)
+        self.m = _EVSET_M[eventset_id] if m is None else int(m)
         self.sysparams = np.asarray(list(sysparams), dtype=np.float64)
         self._h = lib().flint_sys_create(system_id, eventset_id, self.n, self.m, _ptr(self.sysparams), len(self.sysparams))
         if not self._h:

@@ -126,7 +126,21 @@ extern "C" flint_sys_t* flint_sys_create(int system_id, int eventset_id, int n, 
     case FLINT_SYS_CR3BP_SPATIAL: need_n = 6; max_m = 0; break;
     case FLINT_SYS_LORENZ: need_n = 3; max_m = 0; break;
     case FLINT_SYS_TWOBODY: need_n = 6; max_m = 1; break;
-    default: g_last_error = "unknown system_id"; return nullptr;
+    default:
+        if (system_id >= FLINT_SYS_USER_BASE) {            /* registered at build time (csrc/systems.cuh) */
+            const flint::KernelEntry* ke = flint::find_system(system_id);
+            if (!ke) { g_last_error = "flint_sys_create: no user system with this id is compiled into the library"; return nullptr; }
+            if (n != ke->sys_n || m < 0 || m > ke->sys_m_max || m > FLINT_MAX_M || (eventset_id == FLINT_EVSET_NONE && m != 0) ||
+                eventset_id < 0 || nsysparams < 0 || nsysparams > 7) {
+                g_last_error = "flint_sys_create: n/m/eventset do not match the registered user functor";
+                return nullptr;
+            }
+            flint_sys* s = new flint_sys();
+            s->system_id = system_id; s->eventset_id = eventset_id; s->n = n; s->m = m;
+            for (int i = 0; i < 8; ++i) s->sp[i] = (sysparams && i < nsysparams) ? sysparams[i] : 0.0;
+            return s;
+        }
+        g_last_error = "unknown system_id"; return nullptr;
     }
     int ev_m = 0;
     switch (eventset_id) {

@@ -117,9 +117,11 @@ struct KernelEntry {
     occupancy_fn occupancy, occupancy_park;
     void (*load_coefficients)(double* dst);
     int n_state_doubles, n_state_ints;
+    int sys_n, sys_m_max;        /* SYS::N, SYS::M_MAX (validation of user systems in flint_sys_create) */
 };
 void register_kernel(const KernelEntry&);
 const KernelEntry* find_kernel(int method, int system, bool fma, bool events);
+const KernelEntry* find_system(int system);          /* any entry of that system, or NULL */
 int kernel_count();
 
 }  // namespace flint

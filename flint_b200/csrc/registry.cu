@@ -16,6 +16,12 @@ const KernelEntry* find_kernel(int method, int system, bool fma, bool events)
         if (e.method == method && e.system == system && e.fma == fma && e.events == events) return &e;
     return nullptr;
 }
+const KernelEntry* find_system(int system)
+{
+    for (const KernelEntry& e : table())
+        if (e.system == system) return &e;
+    return nullptr;
+}
 int kernel_count() { return (int)table().size(); }
 
 }  // namespace flint

@@ -260,5 +260,26 @@ struct SysTwoBody {
     }
 };
 
+/* ---- user systems ------------------------------------------------------------------------------
+ * A user right-hand side / event function is a struct like the ones above in a header of its own, registered at build
+ * time:  python -m flint_b200.build --user-systems my_systems.cuh   (flint_b200/build.py; tests/user_systems/ has an
+ * example).  Deriving from UserSystem<n, m_max> supplies the bookkeeping of a system whose n derivative components
+ * are all computed from all n states; the struct then provides
+ *     static constexpr int ID = FLINT_SYS_USER_BASE + k;                       the id flint_sys_create() selects
+ *     void load(const double* sp)                                              system parameters (<= 7 doubles)
+ *     template <bool FMA> void accel(const double (&y)[N], double (&f)[N]) const   F  (use madd<FMA> for a*b+c)
+ *     void events(evset, x, y, eval_bits, value, dir, loc_event, action) const      G  (optional)
+ * and the line  FLINT_REGISTER_SYSTEM(Name, has_events)  which the build script reads. */
+#define FLINT_REGISTER_SYSTEM(NAME, HAS_EVENTS)
+template <int N_, int M_MAX_>
+struct UserSystem {
+    static constexpr int N = N_, M_MAX = (M_MAX_ > 0 ? M_MAX_ : 1), NIN = N_, NOUT = N_;
+    static constexpr unsigned ZPLANE = 0;
+    __host__ __device__ static constexpr bool zc(int) { return false; }
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }
+    __host__ __device__ static constexpr int fsrc(int c) { return -2 - c; }
+    __device__ __forceinline__ void events(int, double, double (&)[N_], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
+};
+
 }  // namespace flint
 #endif

@@ -55,7 +55,9 @@ enum {
     FLINT_SYS_CR3BP_PLANAR = 1,  /* tests/test_CR3BP.f90:167-186  sysparams = {mu}              n = 6 */
     FLINT_SYS_CR3BP_SPATIAL = 2, /* tests/test_WP.f90:88-109      sysparams = {mu}              n = 6 */
     FLINT_SYS_LORENZ = 3,        /* tests/test_Lorenz.f90:45-57   sysparams = {sigma,rho,beta}  n = 3 */
-    FLINT_SYS_TWOBODY = 4        /* tests/test_TBP.f90:46-59      sysparams = {GM}              n = 6 */
+    FLINT_SYS_TWOBODY = 4,       /* tests/test_TBP.f90:46-59      sysparams = {GM}              n = 6 */
+    FLINT_SYS_USER_BASE = 100    /* ids >= 100: functors registered at build time (csrc/systems.cuh "user systems");
+                                    their event sets are numbered by the functor itself, m <= its M_MAX */
 };
 enum {
     FLINT_EVSET_NONE = 0,

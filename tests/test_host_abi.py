@@ -156,3 +156,29 @@ def test_c_program_reproduces_the_reference_known_answers(tmp_path):
     st = r["steps"].split()
     assert abs(int(st[2]) - 680) <= 10 and int(r["events"]) == 1
     assert float(r["jacobi_drift"]) < 1e-9
+
+
+def _run_user_system_check():
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "flint_b200", "libflint_b200_user.so")
+    if not os.path.exists(lib):
+        pytest.skip("libflint_b200_user.so not built (python __graft_entry__.py builds it)")
+    env = dict(os.environ, FLINT_B200_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "user_systems", "check_user.py")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_user_registered_systems_host_side():
+    """Build-time registration of user F/G functors: tests/user_systems/example_systems.cuh compiled into its
+    own library; ids, n and m are validated against the registered functor."""
+    assert "OK validation" in _run_user_system_check()
+
+
+@pytest.mark.gpu
+def test_user_registered_systems_on_gpu():
+    """A user-registered Lorenz functor equals the oracle's Lorenz bit for bit; a user Van der Pol oscillator with an upward
+    zero-crossing event agrees with scipy's DOP853 (final state and event times to 1e-8)."""
+    out = _run_user_system_check()
+    assert "OK user Lorenz == oracle Lorenz" in out and "OK user Van der Pol vs scipy" in out
