@@ -741,14 +741,13 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 }
             } else exhausted = true;
         }
-#if FLINT_SYNC_BLOCK
         /* one barrier per step attempt keeps the warps of a CTA in the same part of the loop, so they
          * share instruction-cache fills instead of evicting each other's lines (the hot loop is about the
-         * size of the 32 KB L1.5 instruction cache) */
-        if (__syncthreads_and(!have && exhausted)) break;
-#else
-        if (__all_sync(0xffffffffu, !have && exhausted)) break;
-#endif
+         * size of the 32 KB L1.5 instruction cache).  The smallest loop -- plane variant without events, 27 KB --
+         * fits on its own and runs 2 % faster without the barrier (measured). */
+        constexpr bool kBarrier = FLINT_SYNC_BLOCK && !(EVMODE == 0 && is_plane_variant<SYS>());
+        if (kBarrier) { if (__syncthreads_and(!have && exhausted)) break; }
+        else if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
         if (EVMODE == 1 && pending) {

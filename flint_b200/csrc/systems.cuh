@@ -28,6 +28,7 @@
 #ifndef FLINT_B200_SYSTEMS_CUH
 #define FLINT_B200_SYSTEMS_CUH
 
+#include <type_traits>
 #include "arith.cuh"
 #include "../../include/flint_b200.h"
 
@@ -41,11 +42,7 @@ __device__ __forceinline__ void eval_rhs(const SYS& sys, const double (&y)[SYS::
 #pragma unroll
     for (int i = 0; i < SYS::NIN; ++i) in[i] = y[SYS::in_idx(i)];
     sys.template accel<FMA>(in, out);
-#pragma unroll
-    for (int c = 0; c < SYS::N; ++c) {
-        const int src = SYS::fsrc(c);
-        f[c] = src >= 0 ? y[src >= 0 ? src : 0] : (src == -1 ? 0.0 : out[src <= -2 ? -2 - src : 0]);
-    }
+    sys.template assemble<FMA>(y, out, f);
 }
 
 /* the four CR3BP quotients with the plain operators (cold path of accel) */
@@ -73,16 +70,19 @@ struct SysCR3BPPlanar {
     double mu, omm;   /* omm = 1 - mu (one rounding, as `1.0_WP-mu` at run time; formed on the host, capi.cu) */
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
-    static constexpr int NIN = 4, NOUT = 2;
+    /* out of line: the four quotients (they need only the position); inline (assemble): the Coriolis terms and the
+     * subtractions -- passing the velocities through the call made the callee spill and reload them (ncu: 2.7 % of the
+     * samples on that reload) */
+    static constexpr int NIN = 2, NOUT = 4;
     static constexpr unsigned ZPLANE = (1u << 2) | (1u << 5);   /* z = vz = 0 is invariant under F and under every event action below */
     __host__ __device__ static constexpr bool zc(int) { return false; }
-    __host__ __device__ static constexpr int in_idx(int i) { return i < 2 ? i : i + 1; }          /* y0 y1 y3 y4 */
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }                          /* y0 y1 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : (c == 5 ? -1 : -2 - (c - 3)); }
 
     template <bool FMA>
     __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
     {
-        const double y0 = in[0], y1 = in[1], y3 = in[2], y4 = in[3];
+        const double y0 = in[0], y1 = in[1];
         const double a = y0 + mu;
         const double b = y0 - omm;
         double s1 = __dmul_rn(a, a)   /* == 0 + x*x: x*x is never -0 */;
@@ -101,8 +101,15 @@ struct SysCR3BPPlanar {
             const Quot4 q = cr3bp_quotients_plain(s1, s2, u1, u2, u3, u4);
             q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3];
         }
-        out[0] = (madd<FMA>(2.0, y4, y0) - q1) - q2;
-        out[1] = (madd<FMA>(-2.0, y3, y1) - q3) - q4;
+        out[0] = q1; out[1] = q2; out[2] = q3; out[3] = q4;
+    }
+    template <bool FMA>
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&q)[NOUT], double (&f)[N]) const
+    {
+        f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+        f[3] = (madd<FMA>(2.0, y[4], y[0]) - q[0]) - q[1];
+        f[4] = (madd<FMA>(-2.0, y[3], y[1]) - q[2]) - q[3];
+        f[5] = 0.0;
     }
     template <bool FMA>
     __device__ __forceinline__ void rhs(double /*x*/, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
@@ -152,16 +159,16 @@ struct SysCR3BPSpatial {
     double mu, omm;
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
-    static constexpr int NIN = 5, NOUT = 3;
+    static constexpr int NIN = 3, NOUT = 6;                       /* position in, the six quotients out (see the planar system) */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
-    __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y4 */
+    __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y2 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
 
     template <bool FMA>
     __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
     {
-        const double y0 = in[0], y1 = in[1], y2 = in[2], y3 = in[3], y4 = in[4];
+        const double y0 = in[0], y1 = in[1], y2 = in[2];
         const double a = y0 + mu;
         const double b = y0 - omm;
         double s1 = __dmul_rn(a, a)   /* == 0 + x*x: x*x is never -0 */;
@@ -185,9 +192,15 @@ struct SysCR3BPSpatial {
             const Quot4 z = cr3bp_quotients_plain(s1, s2, u5, u6, u5, u6);
             q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3]; q5 = z.q[0]; q6 = z.q[1];
         }
-        out[0] = (madd<FMA>(2.0, y4, y0) - q1) - q2;
-        out[1] = (madd<FMA>(-2.0, y3, y1) - q3) - q4;
-        out[2] = q5 - q6;
+        out[0] = q1; out[1] = q2; out[2] = q3; out[3] = q4; out[4] = q5; out[5] = q6;
+    }
+    template <bool FMA>
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&q)[NOUT], double (&f)[N]) const
+    {
+        f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+        f[3] = (madd<FMA>(2.0, y[4], y[0]) - q[0]) - q[1];
+        f[4] = (madd<FMA>(-2.0, y[3], y[1]) - q[2]) - q[3];
+        f[5] = q[4] - q[5];
     }
     template <bool FMA>
     __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
@@ -215,6 +228,8 @@ struct SysLorenz {
         f[1] = __dsub_rn(__dmul_rn(y[0], rho - y[2]), y[1]);   /* never fused, in both modes */
         f[2] = madd<FMA>(y[0], y[1], -(beta * y[2]));
     }
+    template <bool FMA>
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<std::remove_cv_t<std::remove_reference_t<decltype(*this)>>>(y, o, f); }
     template <bool FMA>
     __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&)[N], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
@@ -248,6 +263,8 @@ struct SysTwoBody {
         f[0] = fac * y[0]; f[1] = fac * y[1]; f[2] = fac * y[2];
     }
     template <bool FMA>
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<std::remove_cv_t<std::remove_reference_t<decltype(*this)>>>(y, o, f); }
+    template <bool FMA>
     __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&y)[N], unsigned eval_bits, double (&value)[M_MAX],
                                            int (&dir)[M_MAX], int loc_event, int& action) const
@@ -279,6 +296,12 @@ struct UserSystem {
     __host__ __device__ static constexpr int in_idx(int i) { return i; }
     __host__ __device__ static constexpr int fsrc(int c) { return -2 - c; }
     __device__ __forceinline__ void events(int, double, double (&)[N_], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
+    template <bool FMA>
+    __device__ __forceinline__ void assemble(const double (&)[N_], const double (&o)[N_], double (&f)[N_]) const
+    {
+#pragma unroll
+        for (int c = 0; c < N_; ++c) f[c] = o[c];
+    }
 };
 
 }  // namespace flint
