@@ -16,6 +16,7 @@
  *     NOUT                       number of computed derivative components
  *     fsrc(c)                    f[c] = y[fsrc(c)] if >= 0; +0.0 if -1; out[-2 - fsrc(c)] otherwise
  *     accel<FMA>(in, out)        the computed components (branch-free division / square root, arith.cuh)
+ *     INLINE_ACCEL               accel is a handful of operations: inline it at every stage instead of one out-of-line copy
  *     zc(c)                      component c is identically +0.0 in state and derivative (kernel variant for
  *                                trajectories that live in an invariant coordinate plane; false in the general systems)
  *     ZPLANE                     bit mask of the components a plane variant of this system may drop (0: none)
@@ -74,6 +75,7 @@ struct SysCR3BPPlanar {
      * subtractions -- passing the velocities through the call made the callee spill and reload them (ncu: 2.7 % of the
      * samples on that reload) */
     static constexpr int NIN = 2, NOUT = 4;
+    static constexpr bool INLINE_ACCEL = false;
     static constexpr unsigned ZPLANE = (1u << 2) | (1u << 5);   /* z = vz = 0 is invariant under F and under every event action below */
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                          /* y0 y1 */
@@ -160,6 +162,7 @@ struct SysCR3BPSpatial {
     __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
 
     static constexpr int NIN = 3, NOUT = 6;                       /* position in, the six quotients out (see the planar system) */
+    static constexpr bool INLINE_ACCEL = false;
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y2 */
@@ -216,6 +219,7 @@ struct SysLorenz {
     __device__ __forceinline__ void load(const double* sp) { sigma = sp[0]; rho = sp[1]; beta = sp[2]; }
 
     static constexpr int NIN = 3, NOUT = 3;
+    static constexpr bool INLINE_ACCEL = true;                    /* 9 flops */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }
@@ -244,6 +248,7 @@ struct SysTwoBody {
     __device__ __forceinline__ void load(const double* sp) { GM = sp[0]; }
 
     static constexpr int NIN = 3, NOUT = 3;
+    static constexpr bool INLINE_ACCEL = false;
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* position */
@@ -291,6 +296,7 @@ struct SysTwoBody {
 template <int N_, int M_MAX_>
 struct UserSystem {
     static constexpr int N = N_, M_MAX = (M_MAX_ > 0 ? M_MAX_ : 1), NIN = N_, NOUT = N_;
+    static constexpr bool INLINE_ACCEL = false;                   /* a user system may override: true for a very small F */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }
