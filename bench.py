@@ -101,6 +101,10 @@ def run_oracle_sample(arith, n_sample, start=0, nthreads=0):
     import flint_b200 as F
     case = K.cr3bp_case(F.ERK_DOP853, RTOL, arith, max_events=MAX_EVENTS)
     y0 = P.cr3bp_ensemble(n_sample, start=start)
+    if nthreads <= 0:
+        # every host core this process may use -- torch.distributed.run exports OMP_NUM_THREADS=1, which would
+        # silently turn the CPU arm into a single-thread run
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     t0 = time.perf_counter()
     o = case.run_oracle(y0, nthreads=nthreads)
     dt = time.perf_counter() - t0
