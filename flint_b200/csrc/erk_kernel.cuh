@@ -2,7 +2,7 @@
  *
  * Device restatement of ERK_class%Integrate (src/ERKIntegrate.f90:29-802) for N
  * independent trajectories.  B200-first structure, not the reference's loop nest.  The driver is
- * THREE kernels around a per-trajectory state block in HBM (TrajState, SoA over trajectories):
+ * FOUR kernels around a per-trajectory state block in HBM (SoA over trajectories):
  *
  *    erk_init_kernel    one thread per trajectory: argument checks, F0, StepSz0Hairer, first event
  *                       values (:204-259)  ->  state block
@@ -12,6 +12,8 @@
  *                       index appended to a list, the lane takes the next trajectory
  *    erk_event_kernel   one thread per parked trajectory: sub-step scan, Brent, actions, commit of
  *                       the step  ->  state block; the next erk_step_kernel pass resumes them
+ *    erk_dense_kernel   InterpOn: one thread per (trajectory, accepted step): dense-output
+ *                       coefficients from the step the hot loop logged
  *
  * Why: everything that one lane does alone costs 32 lanes.  Measured on the single-kernel version
  * (profiles/r01_notes.md): 7.5 % of the warp instructions ran with < 8 active lanes (event location
@@ -26,11 +28,11 @@
  *    pulls the next index from a global counter, so lanes whose trajectories need
  *    fewer steps do not idle until the slowest lane of the warp is done;
  *  * the adaptive loop is flattened (one step ATTEMPT per warp iteration for every
- *    lane that owns a trajectory), accept/reject is predicated data flow, the
- *    warp leaves the loop on __all_sync(no lane has work);
- *  * state, stage vectors and dense coefficients live in registers (generated
- *    straight-line stage code, erk_methods_gen.cuh); HBM traffic is the SoA
- *    load of Y0 and the SoA store of the results, once per trajectory;
+ *    lane that owns a trajectory), accept/reject is predicated data flow; one CTA-wide barrier per
+ *    attempt (which is also the exit vote) keeps the CTA's warps in the same part of the loop;
+ *  * state and stage vectors live in registers (generated straight-line stage code,
+ *    erk_methods_gen.cuh; KStore below); HBM traffic is the state block and the SoA results,
+ *    a few hundred bytes per trajectory and pass;
  *  * everything rare (sub-step event scanning, Brent root finding, event actions)
  *    is one __noinline__ function working on a context in local memory, so its
  *    register needs do not tax the hot loop.  It REMATERIALISES the stage vectors
@@ -204,14 +206,6 @@ __device__ __forceinline__ void ensure_bip(const SYS& sys, const KArgs& p, EvCtx
     if (!c.bip_counted) { c.fcalls += METHOD::FC_DENSE; c.bip_counted = true; }   /* BipComputed / FCalls as the reference */
     remat_bip<METHOD, SYS, FMA>(sys, p, c);
 }
-/* dense coefficients of an event-truncated step for the InterpOn store (rare) */
-template <class METHOD, class SYS, bool FMA>
-__device__ __noinline__ void rare_dense(const SYS& sys, const KArgs& p, EvCtx<METHOD, SYS>& c)
-{
-    c.haveB = false;
-    remat_bip<METHOD, SYS, FMA>(sys, p, c);
-}
-
 /* Sub-step scanning, event location and action handling (:332-547). */
 template <class METHOD, class SYS, bool FMA>
 __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvCtx<METHOD, SYS>& c, long idx, double hSign)
@@ -405,7 +399,7 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_
         int& fcalls, int acc, double h, double (&Y1)[SYS::N], const double (&F0new)[SYS::N], double Err, double hbyhopt,
         bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N], double& powKey, double& powVal)
 {
-    constexpr int N = SYS::N, PS = METHOD::PSTAR;
+    constexpr int N = SYS::N;
     const long NN = p.N;
     const bool const_step = p.const_step != 0;
     if (dense_mode != 0) {                                              /* :555-566 */
@@ -463,7 +457,7 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_
 template <class METHOD, class SYS, bool FMA>
 __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& p, EvCtx<METHOD, SYS>& c, long idx, double hSign)
 {
-    constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
+    constexpr int M = SYS::M_MAX;
     event_rare_path<METHOD, SYS, FMA>(sys, p, c, idx, hSign);
 #pragma unroll
     for (int i = 0; i < M; ++i) c.EV0[i] = c.EV1[i];                  /* :550 */
@@ -476,7 +470,6 @@ __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& 
     commit_tail<METHOD, SYS, FMA, true>(p, idx, dense ? 1 : 0, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
                                                c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B, pk, pv);
     c.X = Xn; c.h = hio;       /* new X, next step size; new Y in c.Y, new F0 in c.F0old */
-    (void)PS;
 }
 
 /* ===================================================================== trajectory state block */

@@ -404,7 +404,6 @@ def gen_method(E_out, S, M):
     E("for (int c = 0; c < N; ++c) yt[c] = Y0[c];")
     E("ks.template put<0>(F0);")
     E("Err = 0.0;")
-    E("constexpr int nit = DENSE ? NIT_DENSE : NIT;")
     if UNROLLED:
         for it, (kind, st) in enumerate(P.its):
             if it == P.n_int:
