@@ -16,6 +16,7 @@
 
 #include "../../include/flint_b200.h"
 #include "kargs.h"
+#include "arith.cuh"
 
 using flint::KArgs;
 
@@ -415,6 +416,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     }
     /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
     ke->load_coefficients(a.coef);
+    flint::det_pow_constants(a.powc);
     {
         const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = szN * 4;
         const size_t need_b = sd_b + si_b + 2 * li_b + 64;

@@ -436,7 +436,7 @@ __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_
             double pw;
             if (CACHE && hbyhoptOld == powKey) pw = powVal;
             else {
-                pw = det_pow_dev(hbyhoptOld, beta);
+                pw = det_pow_dev(hbyhoptOld, beta, p.powc);
                 if (CACHE) { powKey = hbyhoptOld; powVal = pw; }
             }
             hbyhopt = hbyhopt / pw;
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
         const double dMax = dmax(d1, fabs(d2));
         double h1;
         if (dMax <= 1.0e-15) h1 = dmax(1.0e-6, fabs(h0) * 1.0e-3);
-        else h1 = det_pow_dev(0.01 / dMax, 1.0 / (double)METHOD::P);
+        else h1 = det_pow_dev(0.01 / dMax, 1.0 / (double)METHOD::P, p.powc);
         L.h = L.hSign * dmin(dmin(100.0 * fabs(h0), h1), L.hmax);
         L.fcalls += 1;
     }
@@ -763,7 +763,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             METHOD::template step<SYS, FMA, false>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
             L.total += 1;
             double hbyhopt = 1.0;
-            if (!const_step) hbyhopt = det_pow_dev(Err, expo);            /* src/StepSz.f90:153 */
+            if (!const_step) hbyhopt = det_pow_dev(Err, expo, p.powc);            /* src/StepSz.f90:153 */
             bool parked = false;
             if (Err <= 1.0) {                                               /* :283 */
                 L.fcalls += METHOD::FC_ACC;

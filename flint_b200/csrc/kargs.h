@@ -85,7 +85,8 @@ struct KArgs {
     unsigned long long counter_reset;            /* erk_event_kernel re-arms work_counter with this */
     int* zflag;                                  /* NULL, or: 1 = every trajectory lies in the system's invariant plane (plane-variant kernel runs) */
     unsigned long long* work_counter;
-    double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by launch_erk) */
+    double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by the host, capi.cu) */
+    double powc[32];             /* constants of the controller's pow (arith.cuh: det_pow_constants) */
 };
 
 struct InterpArgs {
