@@ -21,7 +21,23 @@
 #include "arith.cuh"
 #include "kargs.h"
 
+#ifndef FLINT_INTERP_LDS128
+#define FLINT_INTERP_LDS128 0
+#endif
+
 namespace flint {
+
+/* hs * (X - x) < 0 of the reference's cursor test (:88) for hs = +-1: the sign of an IEEE difference of finite numbers is
+ * exact (gradual underflow), so this is X < x for a forward and X > x for a backward integration -- one compare
+ * instead of a subtraction, a product and a compare; NaN compares false either way */
+#ifndef FLINT_INTERP_OLDCMP
+#define FLINT_INTERP_OLDCMP 0
+#endif
+__device__ __forceinline__ bool before(double hs, double X, double x)
+{
+    if (FLINT_INTERP_OLDCMP) return hs * (X - x) < 0.0;
+    return hs > 0.0 ? (X < x) : (X > x);
+}
 
 /* per-trajectory validation of the grid (:60-76): strictly monotone in the direction of
  * integration and inside [Xint(1), Xint(acc+1)] */
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
         int lo = 1, hi = acc;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (hs * (xi[mid] - x) >= 0.0) hi = mid; else lo = mid + 1;
+            if (!before(hs, xi[mid], x) && xi[mid] == xi[mid] && x == x) hi = mid; else lo = mid + 1;
         }
         loc = lo;
     }
@@ -125,12 +141,12 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * a.rstride, xi + loc + 1);
     for (long g = g0; g < g1; ++g) {
         const double x = xs[g - g0];
-        if (loc < acc && hs * (X1 - x) < 0.0) {                       /* forward cursor (:85-103) */
+        if (loc < acc && before(hs, X1, x)) {                         /* forward cursor (:85-103) */
             loc += 1;
             X0 = X1;
             RecBuf<RS>::take(rb, &B[0][0], X1);                       /* the record that was on its way */
-            if (loc < acc && hs * (X1 - x) < 0.0) {                   /* several steps between two grid points: walk Xint */
-                do { loc += 1; X0 = X1; X1 = xi[loc]; } while (loc < acc && hs * (X1 - x) < 0.0);
+            if (loc < acc && before(hs, X1, x)) {                     /* several steps between two grid points: walk Xint */
+                do { loc += 1; X0 = X1; X1 = xi[loc]; } while (loc < acc && before(hs, X1, x));
                 RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * a.rstride, xi + loc);
                 RecBuf<RS>::take(rb, &B[0][0], X1);
             }
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
         int lo = 1, hi = acc;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (hs * (xi[mid] - x) >= 0.0) hi = mid; else lo = mid + 1;
+            if (!before(hs, xi[mid], x) && xi[mid] == xi[mid] && x == x) hi = mid; else lo = mid + 1;
         }
         loc_base = lo;
     }
@@ -249,8 +265,8 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
                 int j = loc_base;                                      /* forward cursor (:85-103), per lane */
                 bool more = false;
                 if (pending) {
-                    while (j < acc && j - win_lo < kWin && hs * (win[j - win_lo] - x) < 0.0) j += 1;
-                    more = j < acc && j - win_lo >= kWin && hs * (win[kWin] - x) < 0.0;     /* the window ended before the step was found */
+                    while (j < acc && j - win_lo < kWin && before(hs, win[j - win_lo], x)) j += 1;
+                    more = j < acc && j - win_lo >= kWin && before(hs, win[kWin], x);     /* the window ended before the step was found */
                 }
                 const bool ok = pending && !more && (j - loc_base) < kRing - kAhead;
                 const unsigned okm = __ballot_sync(FULL, ok);
@@ -297,10 +313,22 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
                     double tk[PS + 1];
                     theta_powers<PS>(theta, tk);
                     const double* __restrict__ B = s_ring[warp][j % kRing];
+                    if (FLINT_INTERP_LDS128 && NI % 2 == 0) {          /* two coefficients per 16-byte shared-memory read */
+                        const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
 #pragma unroll
-                    for (int k = 0; k <= PS; ++k)
+                        for (int k = 0; k <= PS; ++k)
 #pragma unroll
-                        for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
+                            for (int q = 0; q < NI / 2; ++q) {
+                                const double2 b = B2[k * (NI / 2) + q];
+                                y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
+                                y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
+                            }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k <= PS; ++k)
+#pragma unroll
+                            for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
+                    }
                     pending = false;
                 }
                 loc_base = jmax;
