@@ -73,7 +73,7 @@ class _EventsOut(C.Structure):
 
 class _Exec(C.Structure):
     _fields_ = [("mem", C.c_int), ("device", C.c_int), ("stream", C.c_void_p), ("async_", C.c_int),
-                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int)]
+                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int), ("pipeline", C.c_int)]
 
 
 LIB_PATH = os.environ.get("FLINT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflint_b200.so")
@@ -309,7 +309,7 @@ class ERK:
     def IntegrateBatch(self, X0, Y0, Xf, StepSz=None, UseConstStepSz=None, StepAdvance=None, IntStepsOn=None,
                        EventMask=None, EventStates=False, StiffTest=None, params=None, MaxEvents=4, StepsCap=None,
                        out=None, device=0, stream=None, dense_cap=0, block_threads=0, blocks_per_sm=0, want_counters=True,
-                       event_mode=0, plane_variant=0, async_=False):
+                       event_mode=0, plane_variant=0, async_=False, pipeline=0):
         """Y0: (n, N) structure-of-arrays, numpy (host buffers: the call stages H2D/D2H itself) or a
         torch CUDA tensor (device buffers: nothing is copied).  Xf scalar or (N,).  Returns a dict of
         SoA outputs (numpy or torch, matching the input kind).  async_ (device buffers only): return after enqueueing
@@ -339,21 +339,20 @@ class ERK:
             zeros = lambda shape, kw: np.zeros(shape, **kw)  # noqa: E731
             full = lambda shape, v, kw: np.full(shape, v, **kw)  # noqa: E731
             Y0 = np.ascontiguousarray(Y0, dtype=np.float64)
-            xf = np.ascontiguousarray(np.broadcast_to(np.asarray(Xf, dtype=np.float64), (N,))).copy()
             x0v = np.ascontiguousarray(X0, dtype=np.float64) if isinstance(X0, np.ndarray) else None
-            h = None if StepSz is None else np.ascontiguousarray(np.broadcast_to(np.asarray(StepSz, dtype=np.float64), (N,))).copy()
-            stiff = None if StiffTest is None else np.ascontiguousarray(np.broadcast_to(np.asarray(StiffTest, dtype=np.int32), (N,))).copy()
+
+            def inout(key, value, dtype):      # in/out array: the caller's (e.g. pinned) buffer filled in place, or a fresh one
+                if value is None:
+                    return None
+                buf = (out or {}).get(key)
+                if buf is None:
+                    buf = np.empty((N,), dtype=dtype)
+                buf[...] = value
+                return buf
+            xf = inout("Xf", Xf, np.float64)
+            h = inout("StepSz", StepSz, np.float64)
+            stiff = inout("StiffTest", StiffTest, np.int32)
         out = out or {}
-        if not on_dev:      # caller-provided (e.g. pinned) in/out buffers
-            if out.get("Xf") is not None:
-                out["Xf"][:] = xf
-                xf = out["Xf"]
-            if h is not None and out.get("StepSz") is not None:
-                out["StepSz"][:] = h
-                h = out["StepSz"]
-            if stiff is not None and out.get("StiffTest") is not None:
-                out["StiffTest"][:] = stiff
-                stiff = out["StiffTest"]
         yf = out.get("Yf") if out.get("Yf") is not None else zeros((n, N), f64)
         status = out.get("status") if out.get("status") is not None else zeros((N,), i32)
         counters = (out.get("counters") if out.get("counters") is not None else zeros((4, N), i32)) if want_counters else None
@@ -370,7 +369,7 @@ class ERK:
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
         ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, int(bool(async_) and on_dev), int(dense_cap),
-                   int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant))
+                   int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant), int(pipeline))
         x0s = float(X0) if x0v is None else 0.0
         st = lib().flint_erk_integrate_batch(self._h, N, x0s, _ptr(x0v), _ptr(Y0), _ptr(xf), _ptr(yf), _ptr(h), C.byref(io),
                                              _ptr(counters), _ptr(status), C.byref(steps) if steps else None,
@@ -407,7 +406,7 @@ class ERK:
             Xarr = np.ascontiguousarray(np.asarray(Xarr, dtype=np.float64))
             yarr = out if out is not None else np.empty(shape)
             status = np.zeros((N,), dtype=np.int32)
-        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, 0, 0, 0, 0, 0)
+        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, 0, 0, 0, 0, 0, 0)
         st = lib().flint_erk_interpolate_batch(self._h, _ptr(Xarr), G, _ptr(yarr), int(layout), _ptr(status),
                                                int(SaveInterpCoeffs is not None), int(bool(SaveInterpCoeffs)), C.byref(ex))
         self.status = st

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -92,8 +93,11 @@ struct flint_erk {
     double Y0[FLINT_MAX_N]{}, Yf[FLINT_MAX_N]{};
     /* dense storage */
     DenseStore dense;
-    Workspace ws;
-    DevCache stage_int;
+    /* two pipeline slots (host-buffer calls on large ensembles run as chunks on two streams, below); slot 0 serves every other call */
+    Workspace ws[2];
+    DevCache stage_int[2];
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+    int pipe_device = -1;
     bool dense_is_scalar = false;
     bool dense_allocated = false;      /* allocated(me%Xint) */
 };
@@ -169,8 +173,7 @@ extern "C" void flint_erk_destroy(flint_erk_t* e)
 {
     if (!e) return;
     e->dense.release();
-    e->ws.release();
-    e->stage_int.release();
+    for (int k = 0; k < 2; ++k) { e->stage_int[k].release(); e->ws[k].release(); if (e->pipe_stream[k]) cudaStreamDestroy(e->pipe_stream[k]); e->pipe_stream[k] = nullptr; }
     delete e;
 }
 
@@ -284,7 +287,7 @@ struct DevBuf {
 
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
-    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0;
 };
 
 }  // namespace
@@ -354,84 +357,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     a.ev_cap = events_on ? events->cap : 0;
     a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
 
-    DevBuf scratch(me->stage_int, ex.device);
-    cudaStream_t s = ex.stream;
-    const size_t szN = (size_t)N;
-    /* ---- device views of the caller's buffers ---- */
-    if (ex.host) {
-        double* d_y0 = scratch.alloc<double>(szN * n);
-        double* d_xf = scratch.alloc<double>(szN);
-        double* d_yf = scratch.alloc<double>(szN * n);
-        int* d_status = scratch.alloc<int>(szN);
-        if (!d_y0 || !d_xf || !d_yf || !d_status) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
-        bool ok = cuda_ok(cudaMemcpyAsync(d_y0, y0, szN * n * 8, cudaMemcpyHostToDevice, s), "H2D y0") &&
-                  cuda_ok(cudaMemcpyAsync(d_xf, xf, szN * 8, cudaMemcpyHostToDevice, s), "H2D xf");
-        a.y0 = d_y0; a.xf = d_xf; a.yf = d_yf; a.status = d_status;
-        if (x0) { double* d = scratch.alloc<double>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, x0, szN * 8, cudaMemcpyHostToDevice, s), "H2D x0"); a.x0 = d; }
-        if (stepsz) { double* d = scratch.alloc<double>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, stepsz, szN * 8, cudaMemcpyHostToDevice, s), "H2D stepsz"); a.stepsz = d; }
-        if (counters) { a.counters = scratch.alloc<int>(szN * 4); ok = ok && a.counters; }
-        if (stifftest) { int* d = scratch.alloc<int>(szN); ok = ok && d && cuda_ok(cudaMemcpyAsync(d, stifftest, szN * 4, cudaMemcpyHostToDevice, s), "H2D stifftest"); a.stifftest = d; }
-        if (events_on) {
-            a.ev_count = scratch.alloc<int>(szN);
-            a.ev_rec = scratch.alloc<double>(szN * (size_t)(n + 2) * (size_t)a.ev_cap);
-            ok = ok && a.ev_count && a.ev_rec;
-            /* slots the run does not fill read back as NaN (all-ones pattern) */
-            ok = ok && cuda_ok(cudaMemsetAsync(a.ev_rec, 0xFF, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, s), "memset ev_rec");
-        }
-        if (int_steps) {
-            a.xint = scratch.alloc<double>(szN * (size_t)a.steps_cap);
-            a.yint = scratch.alloc<double>(szN * (size_t)a.steps_cap * n);
-            a.steps_count = steps->count ? scratch.alloc<int>(szN) : nullptr;
-            ok = ok && a.xint && a.yint;
-        }
-        if (!ok) return me->status = (g_last_error.empty() ? fail(FLINT_ERROR_MEMALLOC, "device allocation failed") : FLINT_ERROR);
-    } else {
-        a.x0 = x0; a.y0 = y0; a.xf = xf; a.yf = yf; a.stepsz = stepsz; a.counters = counters; a.status = status;
-        a.stifftest = stifftest;
-        if (events_on) { a.ev_count = events->count; a.ev_rec = events->rec; }
-        if (int_steps) { a.xint = steps->xint; a.yint = steps->yint; a.steps_count = steps->count; }
-        if (!status) return me->status = fail(FLINT_ERROR_PARAMS, "status[] is required");
-    }
-    /* ---- dense storage owned by the object (src/ERKInit.f90:321-332: sized for MaxSteps) ---- */
-    if (dense) {
-        long cap = ex.dense_cap > 0 ? ex.dense_cap : me->max_steps;
-        if (cap > me->max_steps) cap = me->max_steps;
-        DenseStore& D = me->dense;
-        /* a step slot holds the step's coefficients, (pstar+1)*nI doubles, and before that its log, 2n+2 doubles */
-        int rstride = me->nI * (me->pstar + 1);
-        if (rstride < 2 * n + 2) rstride = 2 * n + 2;
-        rstride += rstride & 1;
-        if (D.device != ex.device || D.N != N || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || D.rstride != rstride || !D.dxint) {
-            D.release();
-            const size_t nb = szN * (size_t)cap * (size_t)rstride;
-            if (cudaMalloc(&D.dxint, szN * (size_t)(cap + 1) * 8) != cudaSuccess || cudaMalloc(&D.dbip, nb * 8) != cudaSuccess ||
-                cudaMalloc(&D.dcount, szN * 4) != cudaSuccess || cudaMalloc(&D.dflag, szN * (size_t)cap) != cudaSuccess) {
-                cudaGetLastError(); D.release();
-                return me->status = fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; set flint_exec.dense_cap");
-            }
-            D.device = ex.device; D.N = N; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar; D.rstride = rstride;
-        }
-        a.dense_cap = cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dense_count = D.dcount; a.dense_rstride = rstride; a.dflag = D.dflag;
-        me->dense_is_scalar = scalar_call;
-    }
-    /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
     ke->load_coefficients(a.coef);
     flint::det_pow_constants(a.powc);
-    {
-        const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = szN * 4;
-        const size_t need_b = sd_b + si_b + 2 * li_b + 64;
-        Workspace& W = me->ws;
-        if (W.device != ex.device || W.bytes < need_b) {
-            W.release();
-            if (cudaMalloc(&W.ptr, need_b) != cudaSuccess) { cudaGetLastError(); return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed (trajectory state)"); }
-            W.bytes = need_b; W.device = ex.device;
-        }
-        char* base = (char*)W.ptr;
-        a.sd = (double*)base; a.si = (int*)(base + sd_b); a.scap = N;
-    }
-    int* listA = (int*)((char*)me->ws.ptr + szN * (size_t)ke->n_state_doubles * 8 + szN * (size_t)ke->n_state_ints * 4);
-    int* listB = listA + szN;
-    unsigned long long* ctr = (unsigned long long*)(listB + szN + ((szN & 1) ? 1 : 0));   /* 8-byte aligned: [0] work, [1] |A|, [2] |B| */
 
     /* events that are located on (nearly) every step keep the in-loop handling; otherwise park + batch */
     bool park = events_on && ke->step_park && ke->event;
@@ -451,10 +378,6 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     if (!cuda_ok((park ? ke->occupancy_park : ke->occupancy)(&bps, block), "occupancy query")) return me->status = FLINT_ERROR;
     if (bps < 1) bps = 1;
     if (ex.blocks_per_sm > 0 && ex.blocks_per_sm < bps) bps = ex.blocks_per_sm;
-    long grid = (long)dev_sms * bps;
-    const long need = (N + block - 1) / block;
-    if (grid > need) grid = need;
-    const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
     /* plane variant: trajectories with identically zero components (csrc/systems.cuh: SysCR3BPPlanarZ).  The dropped
      * components contribute (0/Sc)^2 to the error norms, so Sc = ATol must be positive there. */
     bool try_plane = ke->step_plane != nullptr && (!events_on || park) && ex.plane_variant != 2;
@@ -463,98 +386,248 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         for (int c = 0; c < n; ++c)
             if (((zp >> c) & 1u) && !(me->atol[me->scalar_tol ? 0 : c] > 0.0)) try_plane = false;
     }
-    const unsigned long long ctr0[4] = {first_free, 0ULL, 0ULL, 1ULL};   /* [3] low word: the plane flag, cleared by erk_init_kernel */
-    if (!cuda_ok(cudaMemcpyAsync(ctr, ctr0, sizeof ctr0, cudaMemcpyHostToDevice, s), "H2D work counters")) return me->status = FLINT_ERROR;
-    a.work_counter = ctr; a.counter_reset = first_free;
-    a.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
-    const int grid_all = (int)((N + 127) / 128);
+
+    /* ---- host buffers, flint_exec.pipeline = k >= 2: the call runs as k chunks of trajectories on two streams, so that the
+     * H2D copy of chunk j+1 and the D2H copy of chunk j-1 travel while chunk j computes (no trajectory depends on another; a
+     * chunk of the SoA arrays is a pitched 2-D copy).  Chunks use the fixed launch schedule of asynchronous calls: no
+     * parked-count read-back, so nothing stalls the host between them.  Off by default: it pays when the copies are a large
+     * part of the call (short integrations); for the north-star configuration (141 ms of compute against 6 ms of copies per
+     * 2^20 orbits) every chunk adds the tails of its two step passes and the call gets slower -- measured, 2^20 orbits:
+     * 151 ms (1 chunk), 152 (2), 162 (4), 182 (8); profiles/r01_notes.md. ---- */
+    long n_chunks = 1;
+    if (ex.host && !dense && !int_steps && !scalar_call && ex.pipeline != 1) {
+        n_chunks = ex.pipeline >= 2 ? ex.pipeline : 1;
+        if (const char* e = getenv("FLINT_B200_PIPE_CHUNKS")) { const long v = atol(e); if (v >= 1) n_chunks = v; }
+        if (n_chunks > N) n_chunks = N;
+        if (n_chunks > 64) n_chunks = 64;
+    }
+    const bool piped = n_chunks > 1;
+    if (piped) {
+        if (me->pipe_device != ex.device)
+            for (int k = 0; k < 2; ++k) { if (me->pipe_stream[k]) cudaStreamDestroy(me->pipe_stream[k]); me->pipe_stream[k] = nullptr; }
+        for (int k = 0; k < 2; ++k)
+            if (!me->pipe_stream[k] && !cuda_ok(cudaStreamCreateWithFlags(&me->pipe_stream[k], cudaStreamNonBlocking), "cudaStreamCreate"))
+                return me->status = FLINT_ERROR;
+        me->pipe_device = ex.device;
+    }
+    const size_t szT = (size_t)N;                                  /* row pitch (elements) of the caller's SoA arrays */
+
+    /* one chunk [off, off + cnt) of the ensemble on stream s with the buffers of pipeline slot `slot` */
+    auto run_chunk = [&](long off, long cnt, int slot, cudaStream_t s, bool fixed_schedule, cudaEvent_t e0, cudaEvent_t e1) -> int {
+        KArgs c = a;
+        c.N = cnt;
+        const size_t szN = (size_t)cnt;
+        /* rows x cnt elements between a compact device array and columns [off, off+cnt) of a host array of pitch N */
+        auto copy2d = [&](void* dst, const void* src, size_t elem, size_t rows, bool to_device, const char* what) -> bool {
+            if (cnt == N)
+                return cuda_ok(cudaMemcpyAsync(dst, src, rows * szN * elem, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s), what);
+            if (to_device)
+                return cuda_ok(cudaMemcpy2DAsync(dst, szN * elem, (const char*)src + (size_t)off * elem, szT * elem, szN * elem, rows,
+                                                 cudaMemcpyHostToDevice, s), what);
+            return cuda_ok(cudaMemcpy2DAsync((char*)dst + (size_t)off * elem, szT * elem, src, szN * elem, szN * elem, rows,
+                                             cudaMemcpyDeviceToHost, s), what);
+        };
+        /* ---- device views of the caller's buffers ---- */
+        if (ex.host) {
+            DevBuf scratch(me->stage_int[slot], ex.device);
+            double* d_y0 = scratch.alloc<double>(szN * n);
+            double* d_xf = scratch.alloc<double>(szN);
+            double* d_yf = scratch.alloc<double>(szN * n);
+            int* d_status = scratch.alloc<int>(szN);
+            if (!d_y0 || !d_xf || !d_yf || !d_status) return fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
+            bool ok = copy2d(d_y0, y0, 8, n, true, "H2D y0") && copy2d(d_xf, xf, 8, 1, true, "H2D xf");
+            c.y0 = d_y0; c.xf = d_xf; c.yf = d_yf; c.status = d_status;
+            if (x0) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, x0, 8, 1, true, "H2D x0"); c.x0 = d; }
+            if (stepsz) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, stepsz, 8, 1, true, "H2D stepsz"); c.stepsz = d; }
+            if (counters) { c.counters = scratch.alloc<int>(szN * 4); ok = ok && c.counters; }
+            if (stifftest) { int* d = scratch.alloc<int>(szN); ok = ok && d && copy2d(d, stifftest, 4, 1, true, "H2D stifftest"); c.stifftest = d; }
+            if (events_on) {
+                c.ev_count = scratch.alloc<int>(szN);
+                c.ev_rec = scratch.alloc<double>(szN * (size_t)(n + 2) * (size_t)c.ev_cap);
+                ok = ok && c.ev_count && c.ev_rec;
+                /* slots the run does not fill read back as NaN (all-ones pattern) */
+                ok = ok && cuda_ok(cudaMemsetAsync(c.ev_rec, 0xFF, szN * (size_t)(n + 2) * (size_t)c.ev_cap * 8, s), "memset ev_rec");
+            }
+            if (int_steps) {
+                c.xint = scratch.alloc<double>(szN * (size_t)c.steps_cap);
+                c.yint = scratch.alloc<double>(szN * (size_t)c.steps_cap * n);
+                c.steps_count = steps->count ? scratch.alloc<int>(szN) : nullptr;
+                ok = ok && c.xint && c.yint;
+            }
+            if (!ok) return g_last_error.empty() ? fail(FLINT_ERROR_MEMALLOC, "device allocation failed") : FLINT_ERROR;
+        } else {
+            c.x0 = x0; c.y0 = y0; c.xf = xf; c.yf = yf; c.stepsz = stepsz; c.counters = counters; c.status = status;
+            c.stifftest = stifftest;
+            if (events_on) { c.ev_count = events->count; c.ev_rec = events->rec; }
+            if (int_steps) { c.xint = steps->xint; c.yint = steps->yint; c.steps_count = steps->count; }
+            if (!status) return fail(FLINT_ERROR_PARAMS, "status[] is required");
+        }
+        /* ---- dense storage owned by the object (src/ERKInit.f90:321-332: sized for MaxSteps) ---- */
+        if (dense) {
+            long cap = ex.dense_cap > 0 ? ex.dense_cap : me->max_steps;
+            if (cap > me->max_steps) cap = me->max_steps;
+            DenseStore& D = me->dense;
+            /* a step slot holds the step's coefficients, (pstar+1)*nI doubles, and before that its log, 2n+2 doubles */
+            int rstride = me->nI * (me->pstar + 1);
+            if (rstride < 2 * n + 2) rstride = 2 * n + 2;
+            rstride += rstride & 1;
+            if (D.device != ex.device || D.N != cnt || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || D.rstride != rstride || !D.dxint) {
+                D.release();
+                const size_t nb = szN * (size_t)cap * (size_t)rstride;
+                if (cudaMalloc(&D.dxint, szN * (size_t)(cap + 1) * 8) != cudaSuccess || cudaMalloc(&D.dbip, nb * 8) != cudaSuccess ||
+                    cudaMalloc(&D.dcount, szN * 4) != cudaSuccess || cudaMalloc(&D.dflag, szN * (size_t)cap) != cudaSuccess) {
+                    cudaGetLastError(); D.release();
+                    return fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; set flint_exec.dense_cap");
+                }
+                D.device = ex.device; D.N = cnt; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar; D.rstride = rstride;
+            }
+            c.dense_cap = cap; c.dxint = D.dxint; c.dbip = D.dbip; c.dense_count = D.dcount; c.dense_rstride = rstride; c.dflag = D.dflag;
+            me->dense_is_scalar = scalar_call;
+        }
+        /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
+        const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = szN * 4;
+        {
+            const size_t need_b = sd_b + si_b + 2 * li_b + 64;
+            Workspace& W = me->ws[slot];
+            if (W.device != ex.device || W.bytes < need_b) {
+                W.release();
+                if (cudaMalloc(&W.ptr, need_b) != cudaSuccess) { cudaGetLastError(); return fail(FLINT_ERROR_MEMALLOC, "device allocation failed (trajectory state)"); }
+                W.bytes = need_b; W.device = ex.device;
+            }
+            char* base = (char*)W.ptr;
+            c.sd = (double*)base; c.si = (int*)(base + sd_b); c.scap = cnt;
+        }
+        int* listA = (int*)((char*)me->ws[slot].ptr + sd_b + si_b);
+        int* listB = listA + szN;
+        unsigned long long* ctr = (unsigned long long*)(listB + szN + ((szN & 1) ? 1 : 0));   /* 8-byte aligned: [0] work, [1] |A|, [2] |B| */
+
+        long grid = (long)dev_sms * bps;
+        const long need = (cnt + block - 1) / block;
+        if (grid > need) grid = need;
+        const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
+        /* [3] low word: the plane flag, cleared by erk_init_kernel (set on the device: a pageable H2D copy would make the
+         * host wait for everything queued on this stream) */
+        if (!cuda_ok(flint::launch_set_counters(ctr, first_free, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
+        g_launches += 1;
+        c.work_counter = ctr; c.counter_reset = first_free;
+        c.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
+        const int grid_all = (int)((cnt + 127) / 128);
+
+        if (e0) cudaEventRecord(e0, s);
+        cudaError_t le = ke->init(c, grid_all, 128, s);
+        g_launches += 1;
+        if (le == cudaSuccess && !park) {
+            c.list_in = nullptr; c.n_in = nullptr; c.list_out = nullptr; c.n_out = nullptr;
+            if (try_plane) { le = ke->step_plane(c, (int)grid, block, s); g_launches += 1; }   /* returns at once unless the flag is set */
+            if (le == cudaSuccess) { le = ke->step(c, (int)grid, block, s); g_launches += 1; }
+        } else if (le == cudaSuccess) {
+            /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
+             * parked count and stop when it is zero; the fixed schedule runs a set number of rounds (empty kernels return
+             * at once).  The last round resumes with in-loop event handling, so it always finishes. */
+            const int max_rounds = fixed_schedule ? 3 : 64;
+            int cur = 1;                                               /* index of the counter of the list being filled */
+            c.list_in = nullptr; c.n_in = nullptr; c.list_out = listA; c.n_out = ctr + 1;
+            if (try_plane) { le = ke->step_plane(c, (int)grid, block, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = ke->step_park(c, (int)grid, block, s); g_launches += 1; }
+            for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
+                long n_parked = cnt;
+                if (!fixed_schedule) {
+                    unsigned long long cc = 0;
+                    if (!cuda_ok(cudaMemcpyAsync(&cc, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
+                        !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
+                    n_parked = (long)cc;
+                    if (n_parked == 0) break;
+                }
+                int* lcur = cur == 1 ? listA : listB;
+                int* loth = cur == 1 ? listB : listA;
+                const int oth = cur == 1 ? 2 : 1;
+                c.list_in = lcur; c.n_in = ctr + cur; c.list_out = loth; c.n_out = ctr + oth;
+                le = ke->event(c, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
+                g_launches += 1;
+                if (le != cudaSuccess) break;
+                long g2 = grid;
+                const long need2 = (n_parked + block - 1) / block;
+                if (!fixed_schedule && g2 > need2) {
+                    /* fewer lanes than the first wave assumed: hand out every item through the counter instead */
+                    g2 = need2 < 1 ? 1 : need2;
+                }
+                if (g2 != grid) {
+                    const unsigned long long ff = (unsigned long long)g2 * (unsigned long long)block;
+                    if (!cuda_ok(cudaMemcpyAsync(ctr, &ff, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) { le = cudaErrorUnknown; break; }
+                }
+                const bool last = round == max_rounds - 1;
+                if (last) { c.zflag = nullptr; le = ke->step(c, (int)g2, block, s); g_launches += 1; }   /* in-loop events, general kernel */
+                else {
+                    if (try_plane) { le = ke->step_plane(c, (int)g2, block, s); g_launches += 1; }
+                    if (le == cudaSuccess) { le = ke->step_park(c, (int)g2, block, s); g_launches += 1; }
+                }
+                cur = oth;
+            }
+        }
+        if (le == cudaSuccess && dense) {                      /* coefficients of the logged steps (erk_kernel.cuh: erk_dense_kernel) */
+            le = ke->dense_coeffs(c, grid_all, 128, s);
+            g_launches += 1;
+        }
+        if (e1) cudaEventRecord(e1, s);
+        if (!cuda_ok(le, "kernel launch")) return FLINT_ERROR;
+
+        if (ex.host) {
+            bool ok = copy2d(xf, c.xf, 8, 1, false, "D2H xf") && copy2d(yf, c.yf, 8, n, false, "D2H yf");
+            if (status) ok = ok && copy2d(status, c.status, 4, 1, false, "D2H status");
+            if (stepsz && !const_step) ok = ok && copy2d(stepsz, c.stepsz, 8, 1, false, "D2H stepsz");
+            if (counters) ok = ok && copy2d(counters, c.counters, 4, 4, false, "D2H counters");
+            if (stifftest) ok = ok && copy2d(stifftest, c.stifftest, 4, 1, false, "D2H stifftest");
+            if (events_on)
+                ok = ok && copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count") &&
+                     copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec");
+            if (int_steps) {
+                ok = ok && copy2d(steps->xint, c.xint, 8, (size_t)c.steps_cap, false, "D2H xint") &&
+                     copy2d(steps->yint, c.yint, 8, (size_t)c.steps_cap * n, false, "D2H yint");
+                if (steps->count) ok = ok && copy2d(steps->count, c.steps_count, 4, 1, false, "D2H steps_count");
+            }
+            if (!ok) return FLINT_ERROR;
+        }
+        return FLINT_SUCCESS;
+    };
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool timed = !ex.async;
-    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-    cudaError_t le = ke->init(a, grid_all, 128, s);
-    g_launches += 1;
-    if (le == cudaSuccess && !park) {
-        a.list_in = nullptr; a.n_in = nullptr; a.list_out = nullptr; a.n_out = nullptr;
-        if (try_plane) { le = ke->step_plane(a, (int)grid, block, s); g_launches += 1; }   /* returns at once unless the flag is set */
-        if (le == cudaSuccess) { le = ke->step(a, (int)grid, block, s); g_launches += 1; }
-    } else if (le == cudaSuccess) {
-        /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
-         * parked count and stop when it is zero; asynchronous calls run a fixed schedule (empty kernels return
-         * at once).  The last round resumes with in-loop event handling, so it always finishes. */
-        const int max_rounds = ex.async ? 3 : 64;
-        int cur = 1;                                               /* index of the counter of the list being filled */
-        a.list_in = nullptr; a.n_in = nullptr; a.list_out = listA; a.n_out = ctr + 1;
-        if (try_plane) { le = ke->step_plane(a, (int)grid, block, s); g_launches += 1; }
-        if (le == cudaSuccess) { le = ke->step_park(a, (int)grid, block, s); g_launches += 1; }
-        for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
-            long n_parked = N;
-            if (!ex.async) {
-                unsigned long long c = 0;
-                if (!cuda_ok(cudaMemcpyAsync(&c, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
-                    !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
-                n_parked = (long)c;
-                if (n_parked == 0) break;
-            }
-            int* lcur = cur == 1 ? listA : listB;
-            int* loth = cur == 1 ? listB : listA;
-            const int oth = cur == 1 ? 2 : 1;
-            a.list_in = lcur; a.n_in = ctr + cur; a.list_out = loth; a.n_out = ctr + oth;
-            le = ke->event(a, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
-            g_launches += 1;
-            if (le != cudaSuccess) break;
-            long g2 = grid;
-            const long need2 = (n_parked + block - 1) / block;
-            if (!ex.async && g2 > need2) {
-                /* fewer lanes than the first wave assumed: hand out every item through the counter instead */
-                g2 = need2 < 1 ? 1 : need2;
-            }
-            if (g2 != grid) {
-                const unsigned long long ff = (unsigned long long)g2 * (unsigned long long)block;
-                if (!cuda_ok(cudaMemcpyAsync(ctr, &ff, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) { le = cudaErrorUnknown; break; }
-            }
-            const bool last = round == max_rounds - 1;
-            if (last) { a.zflag = nullptr; le = ke->step(a, (int)g2, block, s); g_launches += 1; }   /* in-loop events, general kernel */
-            else {
-                if (try_plane) { le = ke->step_plane(a, (int)g2, block, s); g_launches += 1; }
-                if (le == cudaSuccess) { le = ke->step_park(a, (int)g2, block, s); g_launches += 1; }
-            }
-            cur = oth;
+    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    auto drop_events = [&]() { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } };
+    if (!piped) {
+        const int rc = run_chunk(0, N, 0, ex.stream, ex.async, e0, e1);
+        if (rc != FLINT_SUCCESS) { drop_events(); return me->status = rc; }
+        if (!ex.async || ex.host) {
+            if (!cuda_ok(cudaStreamSynchronize(ex.stream), "kernel execution")) { drop_events(); return me->status = FLINT_ERROR; }
         }
-    }
-    if (le == cudaSuccess && dense) {                      /* coefficients of the logged steps (erk_kernel.cuh: erk_dense_kernel) */
-        le = ke->dense_coeffs(a, grid_all, 128, s);
-        g_launches += 1;
-    }
-    if (timed) cudaEventRecord(e1, s);
-    if (!cuda_ok(le, "kernel launch")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
-
-    if (ex.host) {
-        bool ok = cuda_ok(cudaMemcpyAsync(xf, a.xf, szN * 8, cudaMemcpyDeviceToHost, s), "D2H xf") &&
-                  cuda_ok(cudaMemcpyAsync(yf, a.yf, szN * n * 8, cudaMemcpyDeviceToHost, s), "D2H yf");
-        if (status) ok = ok && cuda_ok(cudaMemcpyAsync(status, a.status, szN * 4, cudaMemcpyDeviceToHost, s), "D2H status");
-        if (stepsz && !const_step) ok = ok && cuda_ok(cudaMemcpyAsync(stepsz, a.stepsz, szN * 8, cudaMemcpyDeviceToHost, s), "D2H stepsz");
-        if (counters) ok = ok && cuda_ok(cudaMemcpyAsync(counters, a.counters, szN * 16, cudaMemcpyDeviceToHost, s), "D2H counters");
-        if (stifftest) ok = ok && cuda_ok(cudaMemcpyAsync(stifftest, a.stifftest, szN * 4, cudaMemcpyDeviceToHost, s), "D2H stifftest");
-        if (events_on) {
-            ok = ok && cuda_ok(cudaMemcpyAsync(events->count, a.ev_count, szN * 4, cudaMemcpyDeviceToHost, s), "D2H ev_count") &&
-                 cuda_ok(cudaMemcpyAsync(events->rec, a.ev_rec, szN * (size_t)(n + 2) * (size_t)a.ev_cap * 8, cudaMemcpyDeviceToHost, s), "D2H ev_rec");
+    } else {
+        /* chunk boundaries on multiples of 128 trajectories; the caller's stream is joined on both sides */
+        cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+        cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        cudaEventRecord(fork, ex.stream);
+        for (int k = 0; k < 2; ++k) { cudaStreamWaitEvent(me->pipe_stream[k], fork, 0); cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming); }
+        long per = ((N + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+        int rc = FLINT_SUCCESS, k = 0;
+        for (long off = 0; off < N && rc == FLINT_SUCCESS; off += per, ++k) {
+            const long cnt = off + per <= N ? per : N - off;
+            const bool first = off == 0, last = off + per >= N;
+            rc = run_chunk(off, cnt, k & 1, me->pipe_stream[k & 1], true, first ? e0 : nullptr, nullptr);
+            if (last && rc == FLINT_SUCCESS && timed) {          /* the pipeline's span: first chunk's first kernel .. everything copied back */
+                cudaEventRecord(join[(k & 1) ^ 1], me->pipe_stream[(k & 1) ^ 1]);
+                cudaStreamWaitEvent(me->pipe_stream[k & 1], join[(k & 1) ^ 1], 0);
+                cudaEventRecord(e1, me->pipe_stream[k & 1]);
+            }
         }
-        if (int_steps) {
-            ok = ok && cuda_ok(cudaMemcpyAsync(steps->xint, a.xint, szN * (size_t)a.steps_cap * 8, cudaMemcpyDeviceToHost, s), "D2H xint") &&
-                 cuda_ok(cudaMemcpyAsync(steps->yint, a.yint, szN * (size_t)a.steps_cap * n * 8, cudaMemcpyDeviceToHost, s), "D2H yint");
-            if (steps->count) ok = ok && cuda_ok(cudaMemcpyAsync(steps->count, a.steps_count, szN * 4, cudaMemcpyDeviceToHost, s), "D2H steps_count");
-        }
-        if (!ok) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
-    }
-    if (!ex.async || ex.host) {
-        if (!cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return me->status = FLINT_ERROR; }
+        bool ok = true;
+        for (int q = 0; q < 2; ++q) ok = cuda_ok(cudaStreamSynchronize(me->pipe_stream[q]), "kernel execution") && ok;
+        cudaEventDestroy(fork); cudaEventDestroy(join[0]); cudaEventDestroy(join[1]);
+        if (rc != FLINT_SUCCESS || !ok) { drop_events(); return me->status = (rc != FLINT_SUCCESS ? rc : FLINT_ERROR); }
     }
     if (timed) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         g_last_kernel_ms = ms;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        drop_events();
     }
     return me->status = FLINT_SUCCESS;
 }
@@ -565,7 +638,7 @@ static ExecCtx make_exec(const flint_exec* x)
     if (x) {
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
-        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant;
+        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline;
     }
     return e;
 }

@@ -24,6 +24,20 @@ const KernelEntry* find_system(int system)
 }
 int kernel_count() { return (int)table().size(); }
 
+/* work counters of one Integrate chunk, written in stream order (a pageable host-to-device copy would make the host wait
+ * for everything already queued on the stream) */
+__global__ void set_counters_kernel(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
+                                    unsigned long long c3)
+{
+    ctr[0] = c0; ctr[1] = c1; ctr[2] = c2; ctr[3] = c3;
+}
+cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
+                                unsigned long long c3, cudaStream_t s)
+{
+    set_counters_kernel<<<1, 1, 0, s>>>(ctr, c0, c1, c2, c3);
+    return cudaGetLastError();
+}
+
 }  // namespace flint
 
 extern "C" int flint_b200_kernel_count(void) { return flint::kernel_count(); }

@@ -83,7 +83,7 @@ module FLINT_GPU
         type(c_ptr) :: stream = c_null_ptr
         integer(c_int) :: async = 0
         integer(c_long) :: dense_cap = 0
-        integer(c_int) :: block_threads = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0
+        integer(c_int) :: block_threads = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0
     end type
 
     interface

@@ -148,6 +148,9 @@ typedef struct {
     int plane_variant;  /* 0 = automatic: ensembles whose trajectories all lie in an invariant coordinate plane of the
                            system (planar CR3BP with z = vz = +0) run a kernel that drops the identically-zero
                            components; 2 = never.  Results are identical. */
+    int pipeline;       /* FLINT_MEM_HOST: k >= 2 = the call runs as k chunks of trajectories on two streams, so that the
+                           host<->device copies of one chunk travel while another computes (pays for short integrations,
+                           where the copies are a large part of the call); 0 / 1 = one chunk.  Results are identical. */
 } flint_exec;
 
 /* ---- DiffEqSys ---- */

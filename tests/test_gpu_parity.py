@@ -321,6 +321,22 @@ def test_async_schedule_matches_synchronous_call():
         K.compare_batch(g, o, case, "async")
 
 
+def test_host_pipeline_chunks_match_single_chunk_and_oracle():
+    """FLINT_MEM_HOST with flint_exec.pipeline = k: the ensemble runs as k chunks of trajectories on two streams (pitched
+    H2D / D2H copies of column ranges of the SoA arrays, fixed launch schedule).  Ragged chunk sizes, more chunks than
+    streams, events with one and with many rounds, no events: every output equals the one-chunk call and the oracle."""
+    cases = [(K.cr3bp_case(F.ERK_DOP853, 1e-11, 0), P.cr3bp_ensemble(1000, start=5), (3, 7)),
+             (K.twobody_case(F.ERK_VERNER98R, 1e-10, 0, nper=5, eventset=F.FLINT_EVSET_APSIS, max_events=16), P.perturbed_ensemble(P.TBP_Y0, 300), (2,)),
+             (K.lorenz_case(F.ERK_DOP54, 1e-9, 1, xf=5.0), P.lorenz_ensemble(517), (4,))]
+    for case, y0, chunkings in cases:
+        o = case.run_oracle(y0)
+        one = case.run_gpu(y0, pipeline=1)
+        K.compare_batch(one, o, case, "one chunk")
+        for k in chunkings:
+            g = case.run_gpu(y0, pipeline=k)
+            K.compare_batch(g, o, case, "pipeline=%d" % k)
+
+
 def test_full_size_properties():
     """BASELINE size (2^20 orbits): size-independent properties -- every trajectory succeeds, reaches
     Xf exactly, locates exactly one event of id 2 on the y-axis crossing, Jacobi drift stays at the
