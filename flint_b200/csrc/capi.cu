@@ -565,8 +565,9 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             }
         }
         if (le == cudaSuccess && dense) {                      /* coefficients of the logged steps (erk_kernel.cuh: erk_dense_kernel) */
-            le = ke->dense_coeffs(c, grid_all, 128, s);
-            g_launches += 1;
+            c.zflag = (try_plane && ke->dense_plane) ? (int*)(ctr + 3) : nullptr;
+            if (c.zflag) { le = ke->dense_plane(c, grid_all, 128, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = ke->dense_coeffs(c, grid_all, 128, s); g_launches += 1; }
         }
         if (e1) cudaEventRecord(e1, s);
         if (!cuda_ok(le, "kernel launch")) return FLINT_ERROR;

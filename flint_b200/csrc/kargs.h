@@ -117,6 +117,7 @@ struct KernelEntry {
     launch_fn event;             /* erk_event_kernel (NULL when events == false) */
     launch_fn dense_coeffs;      /* erk_dense_kernel: dense-output coefficients from the step logs */
     launch_fn step_plane;        /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
+    launch_fn dense_plane;       /* plane variant of `dense_coeffs`; NULL if none */
     occupancy_fn occupancy, occupancy_park;
     void (*load_coefficients)(double* dst);
     int n_state_doubles, n_state_ints;
