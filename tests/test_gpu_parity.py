@@ -2,6 +2,8 @@
 on identical seeded inputs.  Bar: BIT-EXACT final states, step sizes, counters, status codes,
 event records and interpolated values (the path is deterministic IEEE arithmetic; see
 DESIGN.md "Arithmetic contract")."""
+import os
+
 import numpy as np
 import pytest
 
@@ -335,6 +337,80 @@ def test_host_pipeline_chunks_match_single_chunk_and_oracle():
         for k in chunkings:
             g = case.run_gpu(y0, pipeline=k)
             K.compare_batch(g, o, case, "pipeline=%d" % k)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("FLINT_FUZZ_SEEDS", "6"))))   # more seeds for a stress run
+def test_randomised_option_combinations_against_the_oracle(seed):
+    """Differential test: seeded random combinations of system, method, arithmetic, tolerances (scalar / vector), event set,
+    event options / step sizes / masks, direction, constant-step, single-step, MaxSteps, natural-step output, stiffness mode,
+    event-handling mode and the host-buffer chunk pipeline -- every output bit for bit equal to the CPU oracle."""
+    rng = np.random.default_rng(20240607 + seed)
+    for trial in range(8):
+        method = int(rng.choice(METHODS))
+        arith = int(rng.integers(0, 2))
+        rtol = float(10.0 ** -rng.integers(6, 12))
+        which = int(rng.integers(0, 4))
+        kw = {}
+        extra = {}
+        if which == 0:                                   # planar CR3BP with one of its event sets
+            evs = int(rng.choice([F.FLINT_EVSET_NONE, F.FLINT_EVSET_CR3BP_SAMPLE3, F.FLINT_EVSET_XY_CROSSING,
+                                  F.FLINT_EVSET_CR3BP_SAMPLE3_TERM, F.FLINT_EVSET_CR3BP_SAMPLE3_RESTART]))
+            if evs in (1, 4, 5):
+                kw.update(event_mask=[int(v) for v in rng.integers(0, 2, 3)],
+                          event_stepsz=[float(rng.choice([0.0, 1e-5, 0.05])), 0.0, float(rng.choice([0.0, 0.1]))],
+                          event_options=[int(v) for v in rng.integers(0, 3, 3)],
+                          event_tol=[1e-3, float(rng.choice([1e-9, 1e-6])), 1e-9])
+            elif evs == 2:
+                kw.update(event_options=[int(v) for v in rng.integers(0, 3, 2)], event_tol=[float(rng.choice([1e-9, 1e-7]))] * 2)
+            case = K.cr3bp_case(method, rtol, arith, eventset=evs, norb=float(rng.choice([0.3, 1.0])), max_events=8, **kw)
+            y0 = P.cr3bp_ensemble(int(rng.integers(40, 200)), start=int(rng.integers(0, 1 << 20)))
+            if rng.integers(0, 3) == 0:
+                y0[2] = 1e-3 * rng.standard_normal(y0.shape[1])       # some members out of the plane: the general kernel
+            if evs != F.FLINT_EVSET_NONE:
+                extra["event_mode"] = int(rng.integers(0, 3))
+        elif which == 1:
+            case = K.lorenz_case(method, rtol, arith, xf=float(rng.choice([2.0, 6.0])))
+            y0 = P.lorenz_ensemble(int(rng.integers(40, 200)), start=int(rng.integers(0, 1 << 20)))
+        elif which == 2:
+            case = K.halo_case(method, rtol, arith)
+            y0 = P.perturbed_ensemble(P.HALO_Y0, int(rng.integers(40, 200)), start=int(rng.integers(0, 1 << 20)))
+        else:
+            evs = int(rng.choice([F.FLINT_EVSET_NONE, F.FLINT_EVSET_APSIS]))
+            case = K.twobody_case(method, rtol, arith, nper=float(rng.choice([0.5, 2.0])), eventset=evs, max_events=8)
+            y0 = P.perturbed_ensemble(P.TBP_Y0, int(rng.integers(40, 200)), start=int(rng.integers(0, 1 << 20)))
+            if rng.integers(0, 2):
+                case.xf = -case.xf                                    # backward
+        N = y0.shape[1]
+        opt = int(rng.integers(0, 6))
+        if opt == 0:
+            case.rtol = rtol * 10.0 ** rng.integers(0, 3, case.n)     # vector tolerances
+            case.atol = case.rtol * 1e-3
+        elif opt == 1:
+            case.step_advance = True
+        elif opt == 2:
+            case.max_steps = int(rng.integers(5, 60))
+        elif opt == 3 and case.interp_on is None:
+            case.int_steps_on = True
+            extra["StepsCap"] = 400
+            case.max_steps = 399
+        elif opt == 4:
+            case.stiff_test = int(rng.integers(0, 3))
+        if rng.integers(0, 3) == 0:
+            case.xf = case.xf * rng.uniform(0.5, 1.0, N)              # ragged end points
+        if rng.integers(0, 2):
+            extra["pipeline"] = int(rng.integers(2, 5))
+        what = "seed %d trial %d: system %d method %d arith %d rtol %g opt %d %r %r" % (seed, trial, which, method, arith, rtol, opt, kw, extra)
+        o = case.run_oracle(y0)
+        g = case.run_gpu(y0, **extra)
+        K.compare_batch(g, o, case, what)
+        if case.int_steps_on:
+            sc = case.oracle_scalar()
+            for t in (0, N // 2, N - 1):
+                r = sc.integrate(case.x0, y0[:, t], float(np.broadcast_to(case.xf, (N,))[t]), io=case.oracle_int(), xint_cap=400)
+                c = int(g["nXint"][t])
+                assert c == r["n_xint"], what
+                K.assert_bit_equal(g["Xint"][:c, t], r["xint"], what + " Xint")
+                K.assert_bit_equal(g["Yint"][:, :c, t].T, r["yint"], what + " Yint")
 
 
 def test_full_size_properties():
