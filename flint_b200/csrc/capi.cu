@@ -368,16 +368,9 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     if (ex.event_mode == 1) park = false;
     if (ex.event_mode == 2 && events_on && ke->step_park) park = true;
 
-    /* persistent lanes: one resident wave, SM count x resident CTAs */
+    /* persistent lanes: the step kernels size themselves (one resident wave of their own CTA size, erk_kernel.cuh: StepCfg) */
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ex.device);
-    int block = ex.block > 0 ? ex.block : FLINT_DEFAULT_BLOCK;
-    block = (block + 31) / 32 * 32;
-    if (block > FLINT_MAX_BLOCK) block = FLINT_MAX_BLOCK;
-    int bps = 0;
-    if (!cuda_ok((park ? ke->occupancy_park : ke->occupancy)(&bps, block), "occupancy query")) return me->status = FLINT_ERROR;
-    if (bps < 1) bps = 1;
-    if (ex.blocks_per_sm > 0 && ex.blocks_per_sm < bps) bps = ex.blocks_per_sm;
     /* plane variant: trajectories with identically zero components (csrc/systems.cuh: SysCR3BPPlanarZ).  The dropped
      * components contribute (0/Sc)^2 to the error norms, so Sc = ATol must be positive there. */
     bool try_plane = ke->step_plane != nullptr && (!events_on || park) && ex.plane_variant != 2;
@@ -501,15 +494,11 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         int* listB = listA + szN;
         unsigned long long* ctr = (unsigned long long*)(listB + szN + ((szN & 1) ? 1 : 0));   /* 8-byte aligned: [0] work, [1] |A|, [2] |B| */
 
-        long grid = (long)dev_sms * bps;
-        const long need = (cnt + block - 1) / block;
-        if (grid > need) grid = need;
-        const unsigned long long first_free = (unsigned long long)grid * (unsigned long long)block;
-        /* [3] low word: the plane flag, cleared by erk_init_kernel (set on the device: a pageable H2D copy would make the
-         * host wait for everything queued on this stream) */
-        if (!cuda_ok(flint::launch_set_counters(ctr, first_free, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
+        /* [0] work counter (every item is handed out through it), [1] |A|, [2] |B|, [3] low word: the plane flag, cleared by
+         * erk_init_kernel.  Set on the device: a pageable H2D copy would make the host wait for everything queued on this stream */
+        if (!cuda_ok(flint::launch_set_counters(ctr, 0ULL, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
         g_launches += 1;
-        c.work_counter = ctr; c.counter_reset = first_free;
+        c.work_counter = ctr;
         c.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
         const int grid_all = (int)((cnt + 127) / 128);
 
@@ -518,8 +507,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         g_launches += 1;
         if (le == cudaSuccess && !park) {
             c.list_in = nullptr; c.n_in = nullptr; c.list_out = nullptr; c.n_out = nullptr;
-            if (try_plane) { le = ke->step_plane(c, (int)grid, block, s); g_launches += 1; }   /* returns at once unless the flag is set */
-            if (le == cudaSuccess) { le = ke->step(c, (int)grid, block, s); g_launches += 1; }
+            if (try_plane) { le = ke->step_plane(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* returns at once unless the flag is set */
+            if (le == cudaSuccess) { le = ke->step(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
         } else if (le == cudaSuccess) {
             /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
              * parked count and stop when it is zero; the fixed schedule runs a set number of rounds (empty kernels return
@@ -527,8 +516,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             const int max_rounds = fixed_schedule ? 3 : 64;
             int cur = 1;                                               /* index of the counter of the list being filled */
             c.list_in = nullptr; c.n_in = nullptr; c.list_out = listA; c.n_out = ctr + 1;
-            if (try_plane) { le = ke->step_plane(c, (int)grid, block, s); g_launches += 1; }
-            if (le == cudaSuccess) { le = ke->step_park(c, (int)grid, block, s); g_launches += 1; }
+            if (try_plane) { le = ke->step_plane(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
             for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
                 long n_parked = cnt;
                 if (!fixed_schedule) {
@@ -545,21 +534,12 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 le = ke->event(c, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
                 g_launches += 1;
                 if (le != cudaSuccess) break;
-                long g2 = grid;
-                const long need2 = (n_parked + block - 1) / block;
-                if (!fixed_schedule && g2 > need2) {
-                    /* fewer lanes than the first wave assumed: hand out every item through the counter instead */
-                    g2 = need2 < 1 ? 1 : need2;
-                }
-                if (g2 != grid) {
-                    const unsigned long long ff = (unsigned long long)g2 * (unsigned long long)block;
-                    if (!cuda_ok(cudaMemcpyAsync(ctr, &ff, 8, cudaMemcpyHostToDevice, s), "H2D work counter")) { le = cudaErrorUnknown; break; }
-                }
+                /* the event kernel re-armed the work counter; a pass never launches more lanes than it has items */
                 const bool last = round == max_rounds - 1;
-                if (last) { c.zflag = nullptr; le = ke->step(c, (int)g2, block, s); g_launches += 1; }   /* in-loop events, general kernel */
+                if (last) { c.zflag = nullptr; le = ke->step(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* in-loop events, general kernel */
                 else {
-                    if (try_plane) { le = ke->step_plane(c, (int)g2, block, s); g_launches += 1; }
-                    if (le == cudaSuccess) { le = ke->step_park(c, (int)g2, block, s); g_launches += 1; }
+                    if (try_plane) { le = ke->step_plane(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                    if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
                 }
                 cur = oth;
             }

@@ -48,6 +48,7 @@
 #ifndef FLINT_B200_ERK_KERNEL_CUH
 #define FLINT_B200_ERK_KERNEL_CUH
 
+#include <type_traits>
 #include "erk_methods_gen.cuh"
 #include "systems.cuh"
 
@@ -116,6 +117,29 @@ __device__ __forceinline__ void brent_root(double a, double b, double ya, double
     niter = itr;
 }
 
+/* ---- launch configuration of erk_step_kernel per system.  A system may declare
+ *   static constexpr int STEP_BLOCK, STEP_MIN_BLOCKS;   CTA size and resident CTAs per SM (__launch_bounds__)
+ *   static constexpr int STEP_BARRIER;                  1: one __syncthreads per step attempt, 0: none
+ * Defaults: 128 x 4 with the barrier.  What is being traded (profiles/r01_notes.md): the hot loop is about the size of the
+ * 32 KB instruction cache of an SM.  Warps that run it in step share instruction fetches; warps in different phases keep the
+ * fp64 pipe busier.  A CTA's warps start together and stay roughly in step on their own; the barrier makes that exact. ---- */
+template <class SYS, class = void> struct has_step_block : std::false_type {};
+template <class SYS> struct has_step_block<SYS, std::void_t<decltype(SYS::STEP_BLOCK)>> : std::true_type {};
+template <class SYS, class = void> struct has_step_barrier : std::false_type {};
+template <class SYS> struct has_step_barrier<SYS, std::void_t<decltype(SYS::STEP_BARRIER)>> : std::true_type {};
+template <class SYS> __host__ __device__ constexpr int step_block()
+{
+    if constexpr (has_step_block<SYS>::value) return SYS::STEP_BLOCK; else return FLINT_BLOCK_THREADS;
+}
+template <class SYS> __host__ __device__ constexpr int step_min_blocks()
+{
+    if constexpr (has_step_block<SYS>::value) return SYS::STEP_MIN_BLOCKS; else return FLINT_MIN_BLOCKS;
+}
+template <class SYS> __host__ __device__ constexpr int step_barrier_value()
+{
+    if constexpr (has_step_barrier<SYS>::value) return SYS::STEP_BARRIER; else return 1;
+}
+
 /* ---- stage-vector store.  Generated code reads k_j[c] as ks.get<slot>(c) and writes a whole vector with
  * ks.put<slot>(f).  Slots in SMEM_MASK live in shared memory ([slot][component][thread]: conflict-free, the
  * offset is an immediate), the others in registers.  Why: at a right-hand-side call the caller holds ~10 live
@@ -145,7 +169,7 @@ struct KStore {
     template <int SLOT> __device__ __forceinline__ double get(int c) const
     {
         if (!comp_stored<SYS>(c)) return 0.0;
-        if constexpr ((SMEM_MASK >> SLOT) & 1u) return s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * FLINT_BLOCK_THREADS];
+        if constexpr ((SMEM_MASK >> SLOT) & 1u) return s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * step_block<SYS>()];
         else return r[SLOT][c];
     }
     template <int SLOT> __device__ __forceinline__ void put(const double (&v)[N])
@@ -153,7 +177,7 @@ struct KStore {
 #pragma unroll
         for (int c = 0; c < N; ++c) {
             if (!comp_stored<SYS>(c)) continue;
-            if constexpr ((SMEM_MASK >> SLOT) & 1u) s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * FLINT_BLOCK_THREADS] = v[c];
+            if constexpr ((SMEM_MASK >> SLOT) & 1u) s[(slot_rank(SMEM_MASK, SLOT) * NC + comp_rank<SYS>(c)) * step_block<SYS>()] = v[c];
             else r[SLOT][c] = v[c];
         }
     }
@@ -164,7 +188,7 @@ struct KStore {
     }
 };
 template <class METHOD, class SYS, unsigned SMEM_MASK>
-constexpr int kstore_smem_bytes() { return slot_rank(SMEM_MASK, 32) * comps_stored<SYS>() * FLINT_BLOCK_THREADS * 8; }
+constexpr int kstore_smem_bytes() { return slot_rank(SMEM_MASK, 32) * comps_stored<SYS>() * step_block<SYS>() * 8; }
 
 /* ---- context of the rare event path (lives in local memory) ---- */
 template <class METHOD, class SYS>
@@ -686,7 +710,7 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
 /* ===================================================================== the hot loop */
 /* EVMODE 0: no events.  1: events located inside the lane loop.  2: steps with events to locate are parked. */
 template <class METHOD, class SYS, bool FMA, int EVMODE>
-__global__ void __launch_bounds__(FLINT_BLOCK_THREADS, FLINT_MIN_BLOCKS)
+__global__ void __launch_bounds__(step_block<SYS>(), step_min_blocks<SYS>())
 erk_step_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
@@ -695,7 +719,6 @@ erk_step_kernel(const __grid_constant__ KArgs p)
     if (p.zflag && ((*p.zflag != 0) != is_plane_variant<SYS>())) return;
     SYS sys;
     sys.load(p.sp);
-    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int m = p.m;
     const bool const_step = p.const_step != 0;
     const double fac = const_step ? 1.0 : kLastStepExpFac;              /* :106-110 */
@@ -704,7 +727,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
     const long n_items = p.list_in ? (long)*p.n_in : p.N;
 
     long idx = -1;
-    bool have = false, exhausted = false, first = true, pending = false;
+    bool have = false, exhausted = false, pending = false;
     Lane<SYS> L;
     L.X = 0; L.h = 0; L.Xf = 0; L.hSign = 1; L.hmax = 0; L.hbyhoptOld = 0;
     L.total = 0; L.acc = 0; L.rej = 0; L.fcalls = 0; L.st = FLINT_SUCCESS;
@@ -724,8 +747,8 @@ erk_step_kernel(const __grid_constant__ KArgs p)
     for (;;) {
         /* ---------------- refill: take the next trajectory from the state block ---------------- */
         if (!have && !exhausted) {
-            const long k = first ? tid : (long)atomicAdd(p.work_counter, 1ULL);
-            first = false;
+            const long k = (long)atomicAdd(p.work_counter, 1ULL);     /* every item through the counter (nvcc aggregates it per warp):
+                                                                         the kernel does not depend on how many lanes were launched */
             if (k < n_items) {
                 const long i = p.list_in ? (long)p.list_in[k] : k;
                 if (i >= 0) {
@@ -740,7 +763,8 @@ erk_step_kernel(const __grid_constant__ KArgs p)
          * fits on its own and runs 2 % faster without the barrier (measured), and so do systems whose right-hand side is a
          * handful of inlined operations (Lorenz DOP54: 83.8 -> 82.4 ms per 2^18 trajectories; with the barrier off two-body
          * DOP853 and the halo orbits lose 3-6 %). */
-        constexpr bool kBarrier = FLINT_SYNC_BLOCK && !(EVMODE == 0 && is_plane_variant<SYS>()) && !(EVMODE == 0 && SYS::INLINE_ACCEL);
+        constexpr bool kBarrier = has_step_barrier<SYS>::value ? (step_barrier_value<SYS>() != 0)
+                                                                : (FLINT_SYNC_BLOCK && !(EVMODE == 0 && SYS::INLINE_ACCEL));
         if (kBarrier) { if (__syncthreads_and(!have && exhausted)) break; }
         else if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
@@ -889,7 +913,7 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
     const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long n_parked = (long)*p.n_in;
     if (j == 0) {                                   /* stream-ordered between two step passes: recycle their counters */
-        *p.work_counter = p.counter_reset;
+        *p.work_counter = 0ULL;
         *p.n_out = 0ULL;
     }
     if (j >= n_parked) return;
@@ -962,15 +986,28 @@ __global__ void __launch_bounds__(128, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense
 
 /* Host-side launchers shared by all instantiations (inst_*.cu). */
 template <class METHOD, class SYS, bool FMA, int EVMODE>
-cudaError_t launch_step(const KArgs& a, int grid, int block, cudaStream_t s)
+cudaError_t launch_step(const KArgs& a, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t s)
 {
     constexpr int smem = kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>();
-    if (smem > 0 && block != FLINT_BLOCK_THREADS) return cudaErrorInvalidConfiguration;   /* the shared-memory layout is compiled for this block size */
-    if (smem > 48 * 1024) {
+    constexpr int BLOCK = step_block<SYS>();
+    int block = (block_req > 0 && block_req < BLOCK) ? (block_req + 31) / 32 * 32 : BLOCK;
+    if (smem > 0) block = BLOCK;                            /* the shared-memory layout is compiled for this block size */
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
         const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
+        attr_set = true;
     }
-    erk_step_kernel<METHOD, SYS, FMA, EVMODE><<<grid, block, smem, s>>>(a);
+    int bps = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block, smem);
+    if (e != cudaSuccess) return e;
+    if (bps < 1) bps = 1;
+    if (bps_req > 0 && bps_req < bps) bps = bps_req;
+    long grid = (long)sm_count * bps;                       /* persistent lanes: one resident wave */
+    const long need = (n_items + block - 1) / block;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    erk_step_kernel<METHOD, SYS, FMA, EVMODE><<<(unsigned)grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <class METHOD, class SYS, bool FMA>
@@ -995,12 +1032,6 @@ cudaError_t launch_dense(const KArgs& a, int grid, int block, cudaStream_t s)
     if (gy > 4096) gy = 4096;
     erk_dense_kernel<METHOD, SYS, FMA><<<dim3((unsigned)grid, (unsigned)gy), block, 0, s>>>(a);
     return cudaGetLastError();
-}
-template <class METHOD, class SYS, bool FMA, int EVMODE>
-cudaError_t occupancy_step(int* blocks_per_sm, int block)
-{
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block,
-                                                         kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>());
 }
 template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }
 

@@ -82,7 +82,6 @@ struct KArgs {
     double* sd; int* si; long scap;              /* [fields][scap] */
     const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */
     int* list_out; unsigned long long* n_out;    /* EVMODE 2: trajectories parked by this pass */
-    unsigned long long counter_reset;            /* erk_event_kernel re-arms work_counter with this */
     int* zflag;                                  /* NULL, or: 1 = every trajectory lies in the system's invariant plane (plane-variant kernel runs) */
     unsigned long long* work_counter;
     double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by the host, capi.cu) */
@@ -107,18 +106,19 @@ cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, 
 
 /* registry of compiled integrate kernels (filled by static initialisers in inst_*.cu) */
 typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t);
-typedef cudaError_t (*occupancy_fn)(int* blocks_per_sm, int block);
+/* the persistent step kernels size themselves: one resident wave of the device (SM count x resident CTAs of the kernel's own
+ * CTA size, erk_kernel.cuh: StepCfg), never more lanes than items; block_req / bps_req > 0 lower the CTA size / the CTAs per SM */
+typedef cudaError_t (*step_launch_fn)(const KArgs&, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t);
 struct KernelEntry {
     int method, system;
     bool fma, events;
     launch_fn init;              /* erk_init_kernel */
-    launch_fn step;              /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
-    launch_fn step_park;         /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
+    step_launch_fn step;         /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
+    step_launch_fn step_park;    /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
     launch_fn event;             /* erk_event_kernel (NULL when events == false) */
     launch_fn dense_coeffs;      /* erk_dense_kernel: dense-output coefficients from the step logs */
-    launch_fn step_plane;        /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
+    step_launch_fn step_plane;   /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
     launch_fn dense_plane;       /* plane variant of `dense_coeffs`; NULL if none */
-    occupancy_fn occupancy, occupancy_park;
     void (*load_coefficients)(double* dst);
     int n_state_doubles, n_state_ints;
     int sys_n, sys_m_max;        /* SYS::N, SYS::M_MAX (validation of user systems in flint_sys_create) */

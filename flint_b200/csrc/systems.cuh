@@ -151,6 +151,17 @@ struct SysCR3BPPlanar {
  * of any result.  erk_init_kernel checks the condition per trajectory; the generic kernel runs otherwise. */
 struct SysCR3BPPlanarZ : SysCR3BPPlanar {
     __host__ __device__ static constexpr bool zc(int c) { return c == 2 || c == 5; }
+#ifndef FLINT_PLANEZ_INLINE
+#define FLINT_PLANEZ_INLINE 1
+#endif
+    static constexpr bool INLINE_ACCEL_HOT = FLINT_PLANEZ_INLINE != 0;   /* arith.cuh: rhs_eval */
+    /* With the right-hand side inlined at every stage the attempt is 2525 instructions instead of 3020, but the hot loop is
+     * 42 KB against a 32 KB instruction cache: one CTA of 16 warps per SM (they start together and stay roughly in step, so
+     * a line is fetched once for all of them) and no barrier (exact lock step starves the fp64 pipe).  Measured, 2^20 orbits,
+     * strict / events: 128 x 4 with barrier 141.6 ms, 256 x 2 with 131.7, 512 x 1 with 139.1, 512 x 1 without 131.3
+     * (out of line, 128 x 4 with barrier: 143.3); without events 131.5 / 126.9 / 119.1 / 119.3 (130.3). */
+    static constexpr int STEP_BLOCK = FLINT_PLANEZ_INLINE ? 512 : 128, STEP_MIN_BLOCKS = FLINT_PLANEZ_INLINE ? 1 : 4;
+    static constexpr int STEP_BARRIER = FLINT_PLANEZ_INLINE ? 0 : 1;
 };
 
 /* ---- spatial CR3BP: tests/test_WP.f90:88-109 (no events in the reference) ---- */
@@ -163,6 +174,7 @@ struct SysCR3BPSpatial {
 
     static constexpr int NIN = 3, NOUT = 6;                       /* position in, the six quotients out (see the planar system) */
     static constexpr bool INLINE_ACCEL = false;
+    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;   /* halo orbit, 2^18: DOP853 13.8 -> 13.4 ms, Verner98R 19.3 -> 18.6 ms against 128 x 4 */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y2 */
@@ -220,6 +232,7 @@ struct SysLorenz {
 
     static constexpr int NIN = 3, NOUT = 3;
     static constexpr bool INLINE_ACCEL = true;                    /* 9 flops */
+    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;   /* DOP54, 2^18 trajectories: 83.8 ms at 128 x 4, 79.6 ms at 256 x 2 */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }

@@ -412,7 +412,7 @@ def gen_method(E_out, S, M):
             E("{   /* %s */" % (("stage %d" % st) if kind == "stage" else "evaluation at (X0+h, Ynew)"))
             E.ind += 1
             emit_iteration_pre(E, P, it, kind, st)
-            E("{ double fv[N]; rhs_eval<SYS, FMA, FLINT_RHS_COPY(%d, %d)>(sys, yt, fv); ks.template put<%d>(fv); }" % (it, len(P.its), P.slot[st]))
+            E("{ double fv[N]; rhs_eval<SYS, FMA, FLINT_RHS_COPY(%d, %d), !DENSE>(sys, yt, fv); ks.template put<%d>(fv); }" % (it, len(P.its), P.slot[st]))
             E.ind -= 1
             E("}")
         if len(P.its) > P.n_int:
