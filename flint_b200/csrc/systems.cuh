@@ -69,13 +69,19 @@ struct SysCR3BPPlanar {
     static constexpr int M_MAX = 3;
     static constexpr int ID = FLINT_SYS_CR3BP_PLANAR;
     double mu, omm;   /* omm = 1 - mu (one rounding, as `1.0_WP-mu` at run time; formed on the host, capi.cu) */
-    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
+    bool pok;         /* both parameters in [2^-60, 2^60): part of the fast-path range test of accel */
+    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; pok = small60(mu) & small60(omm); }
 
     /* out of line: the four quotients (they need only the position); inline (assemble): the Coriolis terms and the
      * subtractions -- passing the velocities through the call made the callee spill and reload them (ncu: 2.7 % of the
      * samples on that reload) */
     static constexpr int NIN = 2, NOUT = 4;
     static constexpr bool INLINE_ACCEL = false;
+    /* general (6-component) kernels, 2^19 orbits, strict, ms with parked events / in-loop events / no events:
+     * out of line 128 x 4 with barrier 85.1 / 114.6 / 75.7; inlined in the hot loop 128 x 4: 85.4 / 129.2 / 74.7,
+     * 256 x 2: 81.4 / 125.5 / 70.5, 512 x 1 without barrier: 80.9 / 115.8 / 67.6 */
+    static constexpr bool INLINE_ACCEL_HOT = true;
+    static constexpr int STEP_BLOCK = 512, STEP_MIN_BLOCKS = 1, STEP_BARRIER = 0;
     static constexpr unsigned ZPLANE = (1u << 2) | (1u << 5);   /* z = vz = 0 is invariant under F and under every event action below */
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                          /* y0 y1 */
@@ -92,7 +98,12 @@ struct SysCR3BPPlanar {
         double s2 = __dmul_rn(b, b);
         s2 = madd<FMA>(y1, y1, s2);
         const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1;
-        const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4);
+        /* fast-path range: s1, s2 in [2^-200, 2^200) and the four numerators in [2^-300, 2^300) -- implied by a, b in
+         * [2^-100, 2^99) (each carries its sum of squares), y1 in [2^-240, 2^99) and the two parameters in [2^-60, 2^60):
+         * 3 tests per call instead of 6 (arith.cuh: small100).  The floor of the other coordinates is as low as the numerators
+         * allow: measured, a 2^-100 floor on y and z sent the halo-orbit ensembles of test_WP to the out-of-line operators often
+         * enough to cost 50 % (12.0 -> 18.3 ms per 2^18 orbits); with 2^-240 they never leave the fast path */
+        const bool ok = small100(a) & small100(b) & small240(y1) & pok;
         double n1, n2, i1, i2;
         sqrt2_nochk(s1, s2, n1, n2);
         const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
@@ -151,17 +162,12 @@ struct SysCR3BPPlanar {
  * of any result.  erk_init_kernel checks the condition per trajectory; the generic kernel runs otherwise. */
 struct SysCR3BPPlanarZ : SysCR3BPPlanar {
     __host__ __device__ static constexpr bool zc(int c) { return c == 2 || c == 5; }
-#ifndef FLINT_PLANEZ_INLINE
-#define FLINT_PLANEZ_INLINE 1
-#endif
-    static constexpr bool INLINE_ACCEL_HOT = FLINT_PLANEZ_INLINE != 0;   /* arith.cuh: rhs_eval */
-    /* With the right-hand side inlined at every stage the attempt is 2525 instructions instead of 3020, but the hot loop is
-     * 42 KB against a 32 KB instruction cache: one CTA of 16 warps per SM (they start together and stay roughly in step, so
-     * a line is fetched once for all of them) and no barrier (exact lock step starves the fp64 pipe).  Measured, 2^20 orbits,
-     * strict / events: 128 x 4 with barrier 141.6 ms, 256 x 2 with 131.7, 512 x 1 with 139.1, 512 x 1 without 131.3
-     * (out of line, 128 x 4 with barrier: 143.3); without events 131.5 / 126.9 / 119.1 / 119.3 (130.3). */
-    static constexpr int STEP_BLOCK = FLINT_PLANEZ_INLINE ? 512 : 128, STEP_MIN_BLOCKS = FLINT_PLANEZ_INLINE ? 1 : 4;
-    static constexpr int STEP_BARRIER = FLINT_PLANEZ_INLINE ? 0 : 1;
+    /* launch configuration inherited (right-hand side inlined in the hot loop, 512 x 1, no barrier).  Inlined, the attempt is
+     * 2525 instructions instead of 3020, but the hot loop is 42 KB against a 32 KB instruction cache: one CTA of 16 warps per
+     * SM (they start together and stay roughly in step, so a line is fetched once for all of them) and no barrier (exact lock
+     * step starves the fp64 pipe).  Measured, 2^20 orbits, strict / events: 128 x 4 with barrier 141.6 ms, 256 x 2 with 131.7,
+     * 512 x 1 with 139.1, 512 x 1 without 131.3 (out of line, 128 x 4 with barrier: 143.3); without events 131.5 / 126.9 /
+     * 119.1 / 119.3 (130.3). */
 };
 
 /* ---- spatial CR3BP: tests/test_WP.f90:88-109 (no events in the reference) ---- */
@@ -170,11 +176,15 @@ struct SysCR3BPSpatial {
     static constexpr int M_MAX = 1;
     static constexpr int ID = FLINT_SYS_CR3BP_SPATIAL;
     double mu, omm;
-    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; }
+    bool pok;
+    __device__ __forceinline__ void load(const double* sp) { mu = sp[0]; omm = sp[7]; pok = small60(mu) & small60(omm); }
 
     static constexpr int NIN = 3, NOUT = 6;                       /* position in, the six quotients out (see the planar system) */
     static constexpr bool INLINE_ACCEL = false;
-    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;   /* halo orbit, 2^18: DOP853 13.8 -> 13.4 ms, Verner98R 19.3 -> 18.6 ms against 128 x 4 */
+    /* halo orbit, 2^18 trajectories, DOP853 / Verner98R ms: out of line 128 x 4: 13.8 / 19.3, 256 x 2: 13.3 / 18.5; inlined in the
+     * hot loop 128 x 4: 13.1 / 19.3, 256 x 2: 12.0 / 18.0, 512 x 1 without barrier: 13.0 / 18.7 */
+    static constexpr bool INLINE_ACCEL_HOT = true;
+    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y2 */
@@ -193,8 +203,7 @@ struct SysCR3BPSpatial {
         s2 = madd<FMA>(y1, y1, s2);
         s2 = madd<FMA>(y2, y2, s2);
         const double u1 = omm * a, u2 = mu * b, u3 = omm * y1, u4 = mu * y1, u5 = -omm * y2, u6 = mu * y2;
-        const bool ok = moderate_sq(s1) & moderate_sq(s2) & moderate(u1) & moderate(u2) & moderate(u3) & moderate(u4) & moderate(u5) &
-                        moderate(u6);
+        const bool ok = small100(a) & small100(b) & small240(y1) & small240(y2) & pok;     /* see the planar system */
         double n1, n2, i1, i2;
         sqrt2_nochk(s1, s2, n1, n2);
         const double r1c = (n1 * n1) * n1, r2c = (n2 * n2) * n2;
@@ -262,6 +271,8 @@ struct SysTwoBody {
 
     static constexpr int NIN = 3, NOUT = 3;
     static constexpr bool INLINE_ACCEL = false;
+    static constexpr bool INLINE_ACCEL_HOT = true;                /* DOP853, 2^17 orbits x 10 periods: 12.8 -> 11.2 ms (128 x 4 with barrier;
+                                                                     256 x 2: 12.5, 512 x 1 without barrier: 11.3) */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* position */
