@@ -133,7 +133,7 @@ def main_reference(a, rank, world):
             "cpu_baseline": {"value": val, "unit": "orbits/s", "cores": threads, "kind": "port",
                              "sample": "%d steps x %d orbits, OpenMP schedule(dynamic,64), one ERK object per thread" % (a.steps, REF_STEP_SAMPLE)},
             "e2e": {"value": val, "unit": "orbits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -269,11 +269,31 @@ def main_ours(a, rank, world, local_rank):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on stdout while the bench runs (e.g. NCCL's version banner) goes to stderr: stdout carries the
+    one JSON line and nothing else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
 
 
 def main():
     a = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -241,7 +241,8 @@ struct SysLorenz {
 
     static constexpr int NIN = 3, NOUT = 3;
     static constexpr bool INLINE_ACCEL = true;                    /* 9 flops */
-    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;   /* DOP54, 2^18 trajectories: 83.8 ms at 128 x 4, 79.6 ms at 256 x 2 */
+    static constexpr int STEP_BLOCK = 256, STEP_MIN_BLOCKS = 2;   /* DOP54, 2^18 trajectories: 83.8 ms at 128 x 4, 79.5 ms at 256 x 2; 256 x 3 (80
+                                                                     registers) 88.8, 256 x 4 (64 registers) 89.2: the lane state spills */
     static constexpr unsigned ZPLANE = 0;
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }
