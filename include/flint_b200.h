@@ -140,8 +140,8 @@ typedef struct {
     void* stream;       /* cudaStream_t or NULL (default stream); the call is synchronous unless async != 0 */
     int async;          /* FLINT_MEM_DEVICE only: return after enqueueing; caller synchronises the stream */
     long dense_cap;     /* dense-output steps stored per trajectory when InterpOn (0 = MaxSteps, as the reference) */
-    int block_threads;  /* 0 = library default */
-    int blocks_per_sm;  /* 0 = library default */
+    int block_threads;  /* 0 = the kernel's own CTA size (a property of the system, 128..512); a smaller multiple of 32 lowers it */
+    int blocks_per_sm;  /* 0 = as many CTAs per SM as are resident; a smaller number lowers it (tuning experiments) */
     int event_mode;     /* how accepted steps with an event to locate are handled: 0 = automatic, 1 = inside the
                            stepping kernel, 2 = parked and located in batches by a separate kernel (the default
                            choice unless an unmasked event has an EventStepSz).  Results are identical. */
