@@ -744,6 +744,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
     KStore<METHOD, SYS, METHOD::SMEM_SLOTS> ks;
     ks.s = flint_smem + threadIdx.x;
 
+    unsigned iter = 0;
     for (;;) {
         /* ---------------- refill: take the next trajectory from the state block ---------------- */
         if (!have && !exhausted) {
@@ -763,9 +764,11 @@ erk_step_kernel(const __grid_constant__ KArgs p)
          * fits on its own and runs 2 % faster without the barrier (measured), and so do systems whose right-hand side is a
          * handful of inlined operations (Lorenz DOP54: 83.8 -> 82.4 ms per 2^18 trajectories; with the barrier off two-body
          * DOP853 and the halo orbits lose 3-6 %). */
-        constexpr bool kBarrier = has_step_barrier<SYS>::value ? (step_barrier_value<SYS>() != 0)
-                                                                : (FLINT_SYNC_BLOCK && !(EVMODE == 0 && SYS::INLINE_ACCEL));
-        if (kBarrier) { if (__syncthreads_and(!have && exhausted)) break; }
+        /* STEP_BARRIER = K: the CTA meets (and votes on its exit) every K-th iteration; 0: never, each warp votes for itself */
+        constexpr int kEvery = has_step_barrier<SYS>::value ? step_barrier_value<SYS>()
+                                                            : ((FLINT_SYNC_BLOCK && !(EVMODE == 0 && SYS::INLINE_ACCEL)) ? 1 : 0);
+        if (kEvery == 1) { if (__syncthreads_and(!have && exhausted)) break; }
+        else if (kEvery > 1) { if ((iter++ % kEvery) == 0 && __syncthreads_and(!have && exhausted)) break; }
         else if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
@@ -998,10 +1001,15 @@ cudaError_t launch_step(const KArgs& a, int sm_count, long n_items, int block_re
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int bps = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block, smem);
-    if (e != cudaSuccess) return e;
-    if (bps < 1) bps = 1;
+    static thread_local int cached_block = -1, cached_bps = 0;   /* one occupancy query per CTA size and host thread */
+    if (cached_block != block) {
+        int q = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block, smem);
+        if (e != cudaSuccess) return e;
+        cached_bps = q < 1 ? 1 : q;
+        cached_block = block;
+    }
+    int bps = cached_bps;
     if (bps_req > 0 && bps_req < bps) bps = bps_req;
     long grid = (long)sm_count * bps;                       /* persistent lanes: one resident wave */
     const long need = (n_items + block - 1) / block;
