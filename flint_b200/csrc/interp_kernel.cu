@@ -199,6 +199,48 @@ static cudaError_t launch_soa_one(const InterpArgs& a, dim3 grid, cudaStream_t s
  * a small shared-memory ring with coalesced 16-byte loads and read back with LDS, where lanes on the same step
  * broadcast.  A block is 8 warps = 8 trajectories on the same grid batch, so the [nI][G][N] layout can be written
  * as 64-byte rows (8 trajectories x 8 bytes: whole sectors) through a shared-memory transpose. */
+/* one step record, RS doubles, from HBM into a shared-memory ring slot: coalesced 16-byte cp.async by the warp's lanes */
+template <int RS>
+__device__ __forceinline__ void fetch_record(const double* __restrict__ r, double* d, int lane)
+{
+    if (RS % 2 == 0) {
+        if (lane < RS / 2) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + 2 * lane);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r + 2 * lane));
+        }
+    } else {
+        for (int q = lane; q < RS; q += 32) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(r + q));
+        }
+    }
+}
+/* InterpY (src/ERKInterp.f90:124-140) for one point of the step [X0, X1] whose coefficients B[k][ii] sit in shared memory */
+template <bool FMA, int PS, int NI>
+__device__ __forceinline__ void eval_point(double X0, double X1, double x, const double* __restrict__ B, double (&y)[NI])
+{
+    const double h = X1 - X0;
+    const double theta = (x - X0) / h;
+    double tk[PS + 1];
+    theta_powers<PS>(theta, tk);
+    if (FLINT_INTERP_LDS128 && NI % 2 == 0) {          /* two coefficients per 16-byte shared-memory read */
+        const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
+#pragma unroll
+        for (int k = 0; k <= PS; ++k)
+#pragma unroll
+            for (int q = 0; q < NI / 2; ++q) {
+                const double2 b = B2[k * (NI / 2) + q];
+                y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
+                y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
+            }
+    } else {
+#pragma unroll
+        for (int k = 0; k <= PS; ++k)
+#pragma unroll
+            for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
+    }
+}
+
 constexpr int kTW = 8;          /* trajectories (warps) per block */
 constexpr int kRing = 8;        /* step records resident (or on their way) per warp */
 constexpr int kAhead = 3;       /* records requested beyond the ones a batch needs: they arrive while it is evaluated */
@@ -285,21 +327,7 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
                 int want_hi = jmax + 1 + kAhead;
                 if (want_hi > acc + 1) want_hi = acc + 1;
                 __syncwarp();                                          /* nobody still reads the slots about to be overwritten */
-                for (int sidx = ring_hi; sidx < want_hi; ++sidx) {
-                    const double* __restrict__ r = rec0 + (long)(sidx - 1) * a.rstride;
-                    double* d = s_ring[warp][sidx % kRing];
-                    if (RS % 2 == 0) {
-                        if (lane < RS / 2) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + 2 * lane);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r + 2 * lane));
-                        }
-                    } else {
-                        for (int q = lane; q < RS; q += 32) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + q);
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(r + q));
-                        }
-                    }
-                }
+                for (int sidx = ring_hi; sidx < want_hi; ++sidx) fetch_record<RS>(rec0 + (long)(sidx - 1) * a.rstride, s_ring[warp][sidx % kRing], lane);
                 asm volatile("cp.async.commit_group;");
                 if (want_hi > ring_hi) ring_hi = want_hi;
                 if (ring_hi - ring_lo > kRing) ring_lo = ring_hi - kRing;
@@ -307,28 +335,7 @@ __global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
                 else asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
                 if (ok) {
-                    const double X0 = win[j - 1 - win_lo], X1 = win[j - win_lo];
-                    const double h = X1 - X0;
-                    const double theta = (x - X0) / h;
-                    double tk[PS + 1];
-                    theta_powers<PS>(theta, tk);
-                    const double* __restrict__ B = s_ring[warp][j % kRing];
-                    if (FLINT_INTERP_LDS128 && NI % 2 == 0) {          /* two coefficients per 16-byte shared-memory read */
-                        const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
-#pragma unroll
-                        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-                            for (int q = 0; q < NI / 2; ++q) {
-                                const double2 b = B2[k * (NI / 2) + q];
-                                y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
-                                y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
-                            }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-                            for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
-                    }
+                    eval_point<FMA, PS, NI>(win[j - 1 - win_lo], win[j - win_lo], x, s_ring[warp][j % kRing], y);
                     pending = false;
                 }
                 loc_base = jmax;
