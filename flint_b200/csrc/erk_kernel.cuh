@@ -768,7 +768,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         constexpr int kEvery = has_step_barrier<SYS>::value ? step_barrier_value<SYS>()
                                                             : ((FLINT_SYNC_BLOCK && !(EVMODE == 0 && SYS::INLINE_ACCEL)) ? 1 : 0);
         if (kEvery == 1) { if (__syncthreads_and(!have && exhausted)) break; }
-        else if (kEvery > 1) { if ((iter++ % kEvery) == 0 && __syncthreads_and(!have && exhausted)) break; }
+        else if (kEvery > 1) { if ((iter++ % (unsigned)(kEvery > 1 ? kEvery : 2)) == 0 && __syncthreads_and(!have && exhausted)) break; }
         else if (__all_sync(0xffffffffu, !have && exhausted)) break;
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
