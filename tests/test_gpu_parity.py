@@ -323,6 +323,20 @@ def test_async_schedule_matches_synchronous_call():
         K.compare_batch(g, o, case, "async")
 
 
+def test_results_do_not_depend_on_the_launch_shape():
+    """flint_exec.block_threads / blocks_per_sm lower the CTA size / the resident CTAs of the persistent step kernels (whose own
+    shape is a property of the system: 512 x 1, 256 x 2 or 128 x 4); every item goes through the work counter, so any shape
+    gives the same bits."""
+    cases = [(K.cr3bp_case(F.ERK_DOP853, 1e-11, 0), P.cr3bp_ensemble(3000, start=11)),
+             (K.halo_case(F.ERK_VERNER98R, 1e-9, 1), P.perturbed_ensemble(P.HALO_Y0, 700)),
+             (K.lorenz_case(F.ERK_DOP54, 1e-9, 0, xf=5.0), P.lorenz_ensemble(900))]
+    for case, y0 in cases:
+        o = case.run_oracle(y0)
+        for kw in (dict(), dict(block_threads=32), dict(block_threads=128, blocks_per_sm=1), dict(block_threads=96, blocks_per_sm=3),
+                   dict(blocks_per_sm=1), dict(block_threads=1024)):
+            K.compare_batch(case.run_gpu(y0, **kw), o, case, "launch shape %r" % (kw,))
+
+
 def test_host_pipeline_chunks_match_single_chunk_and_oracle():
     """FLINT_MEM_HOST with flint_exec.pipeline = k: the ensemble runs as k chunks of trajectories on two streams (pitched
     H2D / D2H copies of column ranges of the SoA arrays, fixed launch schedule).  Ragged chunk sizes, more chunks than
