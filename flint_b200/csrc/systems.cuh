@@ -317,7 +317,12 @@ struct SysTwoBody {
  *     void load(const double* sp)                                              system parameters (<= 7 doubles)
  *     template <bool FMA> void accel(const double (&y)[N], double (&f)[N]) const   F  (use madd<FMA> for a*b+c)
  *     void events(evset, x, y, eval_bits, value, dir, loc_event, action) const      G  (optional)
- * and the line  FLINT_REGISTER_SYSTEM(Name, has_events)  which the build script reads. */
+ * and the line  FLINT_REGISTER_SYSTEM(Name, has_events)  which the build script reads.  Optional tuning members (defaults in
+ * parentheses; measured per built-in system above):
+ *     static constexpr bool INLINE_ACCEL      (false)  inline accel everywhere: a right-hand side of a handful of operations
+ *     static constexpr bool INLINE_ACCEL_HOT  (absent = false)  inline it in the hot step kernel only
+ *     static constexpr int  STEP_BLOCK, STEP_MIN_BLOCKS  (128, 4)  CTA size and resident CTAs of the step kernel
+ *     static constexpr int  STEP_BARRIER      (absent: 1, or 0 without events when INLINE_ACCEL)  CTA barrier every K-th attempt */
 #define FLINT_REGISTER_SYSTEM(NAME, HAS_EVENTS)
 template <int N_, int M_MAX_>
 struct UserSystem {
