@@ -395,7 +395,11 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         if (n_chunks > 64) n_chunks = 64;
     }
     const bool piped = n_chunks > 1;
-    if (piped) {
+    /* Host buffers with parked events: the event records are append-only, and in the common case (every event masked after its
+     * first trigger) they are complete after the first event kernel.  They are copied back on a second stream while the
+     * resume pass computes; if any count changed afterwards they are copied again at the end (profiles/r01_notes.md). */
+    const bool early_ev = ex.host && events_on && park && !piped && !ex.async && getenv("FLINT_B200_NO_EARLY_EVENTS") == nullptr;
+    if (piped || early_ev) {
         if (me->pipe_device != ex.device)
             for (int k = 0; k < 2; ++k) { if (me->pipe_stream[k]) cudaStreamDestroy(me->pipe_stream[k]); me->pipe_stream[k] = nullptr; }
         for (int k = 0; k < 2; ++k)
@@ -410,6 +414,9 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         KArgs c = a;
         c.N = cnt;
         const size_t szN = (size_t)cnt;
+        int* ev_snap = nullptr;                     /* event counts at the time of the early copy */
+        bool early_done = false;
+        cudaEvent_t ev_ready = nullptr;
         /* rows x cnt elements between a compact device array and columns [off, off+cnt) of a host array of pitch N */
         auto copy2d = [&](void* dst, const void* src, size_t elem, size_t rows, bool to_device, const char* what) -> bool {
             if (cnt == N)
@@ -440,6 +447,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 ok = ok && c.ev_count && c.ev_rec;
                 /* slots the run does not fill read back as NaN (all-ones pattern) */
                 ok = ok && cuda_ok(cudaMemsetAsync(c.ev_rec, 0xFF, szN * (size_t)(n + 2) * (size_t)c.ev_cap * 8, s), "memset ev_rec");
+                if (early_ev) { ev_snap = scratch.alloc<int>(szN); ok = ok && ev_snap; }
             }
             if (int_steps) {
                 c.xint = scratch.alloc<double>(szN * (size_t)c.steps_cap);
@@ -498,6 +506,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
          * erk_init_kernel.  Set on the device: a pageable H2D copy would make the host wait for everything queued on this stream */
         if (!cuda_ok(flint::launch_set_counters(ctr, 0ULL, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
         g_launches += 1;
+        if (early_ev && !cuda_ok(cudaMemsetAsync(ctr + 4, 0, 8, s), "memset flag")) return FLINT_ERROR;   /* [4]: event counts changed after the early copy */
         c.work_counter = ctr;
         c.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
         const int grid_all = (int)((cnt + 127) / 128);
@@ -534,12 +543,29 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 le = ke->event(c, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
                 g_launches += 1;
                 if (le != cudaSuccess) break;
+                bool issue_early = false;
+                if (early_ev && round == 0 && ev_snap) {       /* stream order: snapshot and marker before the resume pass */
+                    const bool ok = cuda_ok(cudaMemcpyAsync(ev_snap, c.ev_count, szN * 4, cudaMemcpyDeviceToDevice, s), "snapshot of the event counts") &&
+                                    cuda_ok(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming), "cudaEventCreate") &&
+                                    cuda_ok(cudaEventRecord(ev_ready, s), "cudaEventRecord");
+                    if (!ok) { le = cudaErrorUnknown; break; }
+                    issue_early = true;
+                }
                 /* the event kernel re-armed the work counter; a pass never launches more lanes than it has items */
                 const bool last = round == max_rounds - 1;
                 if (last) { c.zflag = nullptr; le = ke->step(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* in-loop events, general kernel */
                 else {
                     if (try_plane) { le = ke->step_plane(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
                     if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                }
+                if (issue_early && le == cudaSuccess) {        /* issued after the launch: a pageable destination blocks the host, not the GPU */
+                    cudaStream_t s2 = me->pipe_stream[1];
+                    const bool ok = cuda_ok(cudaStreamWaitEvent(s2, ev_ready, 0), "cudaStreamWaitEvent") &&
+                                    cuda_ok(cudaMemcpyAsync(events->count, ev_snap, szN * 4, cudaMemcpyDeviceToHost, s2), "early D2H ev_count") &&
+                                    cuda_ok(cudaMemcpyAsync(events->rec, c.ev_rec, szN * (size_t)(n + 2) * (size_t)c.ev_cap * 8, cudaMemcpyDeviceToHost, s2),
+                                            "early D2H ev_rec");
+                    if (!ok) { le = cudaErrorUnknown; break; }
+                    early_done = true;
                 }
                 cur = oth;
             }
@@ -550,7 +576,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             if (le == cudaSuccess) { le = ke->dense_coeffs(c, grid_all, 128, s); g_launches += 1; }
         }
         if (e1) cudaEventRecord(e1, s);
-        if (!cuda_ok(le, "kernel launch")) return FLINT_ERROR;
+        if (!cuda_ok(le, "kernel launch")) { if (ev_ready) cudaEventDestroy(ev_ready); return FLINT_ERROR; }
 
         if (ex.host) {
             bool ok = copy2d(xf, c.xf, 8, 1, false, "D2H xf") && copy2d(yf, c.yf, 8, n, false, "D2H yf");
@@ -558,7 +584,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             if (stepsz && !const_step) ok = ok && copy2d(stepsz, c.stepsz, 8, 1, false, "D2H stepsz");
             if (counters) ok = ok && copy2d(counters, c.counters, 4, 4, false, "D2H counters");
             if (stifftest) ok = ok && copy2d(stifftest, c.stifftest, 4, 1, false, "D2H stifftest");
-            if (events_on)
+            if (events_on && !early_done)
                 ok = ok && copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count") &&
                      copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec");
             if (int_steps) {
@@ -566,8 +592,21 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                      copy2d(steps->yint, c.yint, 8, (size_t)c.steps_cap * n, false, "D2H yint");
                 if (steps->count) ok = ok && copy2d(steps->count, c.steps_count, 4, 1, false, "D2H steps_count");
             }
+            if (ok && early_done) {
+                /* did any trajectory record another event after the early copy?  then the records travel again */
+                unsigned long long changed = 0;
+                ok = cuda_ok(flint::launch_any_differs(c.ev_count, ev_snap, cnt, ctr + 4, s), "event count check") &&
+                     cuda_ok(cudaMemcpyAsync(&changed, ctr + 4, 8, cudaMemcpyDeviceToHost, s), "D2H event flag") &&
+                     cuda_ok(cudaStreamSynchronize(s), "kernel execution") &&
+                     cuda_ok(cudaStreamSynchronize(me->pipe_stream[1]), "early event copy");
+                g_launches += 1;
+                if (ok && changed)
+                    ok = copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count") &&
+                         copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec");
+            }
+            if (ev_ready) cudaEventDestroy(ev_ready);
             if (!ok) return FLINT_ERROR;
-        }
+        } else if (ev_ready) cudaEventDestroy(ev_ready);
         return FLINT_SUCCESS;
     };
 

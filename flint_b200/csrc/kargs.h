@@ -103,6 +103,7 @@ struct InterpArgs {
 cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
 cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
                                 unsigned long long c3, cudaStream_t);   /* registry.cu */
+cudaError_t launch_any_differs(const int* a, const int* b, long n, unsigned long long* flag, cudaStream_t);
 
 /* registry of compiled integrate kernels (filled by static initialisers in inst_*.cu) */
 typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t);
