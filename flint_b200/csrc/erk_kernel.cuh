@@ -220,7 +220,7 @@ __device__ __forceinline__ void remat_bip(const SYS& sys, const KArgs& p, EvCtx<
     KStore<METHOD, SYS, 0u> ks;
     ks.s = nullptr;
     double Yn[N], Yp[N], e;
-    METHOD::template step<SYS, FMA, true>(sys, c.X, c.Y, c.F0old, c.h_stage, c.h, ks, Yn, Yp, p.tol, false, e, p.coef);
+    METHOD::template step<SYS, FMA, true, false>(sys, c.X, c.Y, c.F0old, c.h_stage, c.h, ks, Yn, Yp, p.tol, false, e, p.coef);
     METHOD::template dense_coeffs<SYS, FMA>(ks, c.Y, c.h, c.Y1, c.B, p.coef);
     c.haveB = true;
 }
@@ -789,7 +789,13 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             if (L.hSign * (madd<FMA>(fac, L.h, L.X) - L.Xf) > 0.0) { L.h = L.Xf - L.X; L.LAST = true; }   /* :268-271 */
             const double h = L.h;
             double Ynew[N], Ypre[N], Err;
-            METHOD::template step<SYS, FMA, false>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
+            METHOD::template step<SYS, FMA, false, true>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);   /* :274 */
+            if constexpr (lazy_range<SYS>::value) {
+                if (sys.bad) {      /* an operand left the range of the branch-free operators: the attempt again, stage-by-stage fallback */
+                    sys.bad = false;
+                    METHOD::template step<SYS, FMA, false, false>(sys, L.X, L.Y, L.F0, h, h, ks, Ynew, Ypre, p.tol, !const_step, Err, p.coef);
+                }
+            }
             L.total += 1;
             double hbyhopt = 1.0;
             if (!const_step) hbyhopt = det_pow_dev(Err, expo, p.powc);            /* src/StepSz.f90:153 */
@@ -981,7 +987,7 @@ __global__ void __launch_bounds__(128, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense
         for (int c = 0; c < N; ++c) { Y[c] = rec[2 + c]; F0[c] = rec[2 + N + c]; }
         KStore<METHOD, SYS, 0u> ks;
         ks.s = nullptr;
-        METHOD::template step<SYS, FMA, true>(sys, X, Y, F0, h, h, ks, Yn, Yp, p.tol, false, e, p.coef);
+        METHOD::template step<SYS, FMA, true, false>(sys, X, Y, F0, h, h, ks, Yn, Yp, p.tol, false, e, p.coef);
         METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Yn, B, p.coef);
         store_dense_record<METHOD, SYS>(p, t, s + 1, B);
     }

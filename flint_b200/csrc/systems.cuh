@@ -88,8 +88,12 @@ struct SysCR3BPPlanar {
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                          /* y0 y1 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : (c == 5 ? -1 : -2 - (c - 3)); }
 
-    template <bool FMA>
-    __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
+    static constexpr bool LAZY_RANGE = true;
+    mutable bool bad = false;                                     /* accel_lazy: an operand left the fast-path range during this attempt */
+    template <bool FMA> __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const { accel_impl<FMA, false>(in, out); }
+    template <bool FMA> __device__ __forceinline__ void accel_lazy(const double (&in)[NIN], double (&out)[NOUT]) const { accel_impl<FMA, true>(in, out); }
+    template <bool FMA, bool LAZY>
+    __device__ __forceinline__ void accel_impl(const double (&in)[NIN], double (&out)[NOUT]) const
     {
         const double y0 = in[0], y1 = in[1];
         const double a = y0 + mu;
@@ -111,7 +115,8 @@ struct SysCR3BPPlanar {
         rcp2_newton(r1c, r2c, i1, i2);
         double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
         double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
-        if (!ok) {                                   /* operands outside the fast-path range: plain operators, out of line */
+        if (LAZY) bad = bad | !ok;                   /* the lane loop repeats the attempt through accel */
+        else if (!ok) {                              /* operands outside the fast-path range: plain operators, out of line */
             const Quot4 q = cr3bp_quotients_plain(s1, s2, u1, u2, u3, u4);
             q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3];
         }
@@ -191,8 +196,12 @@ struct SysCR3BPSpatial {
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* y0..y2 */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
 
-    template <bool FMA>
-    __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const
+    static constexpr bool LAZY_RANGE = true;
+    mutable bool bad = false;
+    template <bool FMA> __device__ __forceinline__ void accel(const double (&in)[NIN], double (&out)[NOUT]) const { accel_impl<FMA, false>(in, out); }
+    template <bool FMA> __device__ __forceinline__ void accel_lazy(const double (&in)[NIN], double (&out)[NOUT]) const { accel_impl<FMA, true>(in, out); }
+    template <bool FMA, bool LAZY>
+    __device__ __forceinline__ void accel_impl(const double (&in)[NIN], double (&out)[NOUT]) const
     {
         const double y0 = in[0], y1 = in[1], y2 = in[2];
         const double a = y0 + mu;
@@ -212,7 +221,8 @@ struct SysCR3BPSpatial {
         double q1 = div_rcp_nochk(u1, r1c, i1), q2 = div_rcp_nochk(u2, r2c, i2);
         double q3 = div_rcp_nochk(u3, r1c, i1), q4 = div_rcp_nochk(u4, r2c, i2);
         double q5 = div_rcp_nochk(u5, r1c, i1), q6 = div_rcp_nochk(u6, r2c, i2);
-        if (!ok) {                                   /* operands outside the fast-path range: plain operators, out of line */
+        if (LAZY) bad = bad | !ok;
+        else if (!ok) {                              /* operands outside the fast-path range: plain operators, out of line */
             const Quot4 q = cr3bp_quotients_plain(s1, s2, u1, u2, u3, u4);
             const Quot4 z = cr3bp_quotients_plain(s1, s2, u5, u6, u5, u6);
             q1 = q.q[0]; q2 = q.q[1]; q3 = q.q[2]; q4 = q.q[3]; q5 = z.q[0]; q6 = z.q[1];

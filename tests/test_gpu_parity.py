@@ -337,6 +337,26 @@ def test_results_do_not_depend_on_the_launch_shape():
             K.compare_batch(case.run_gpu(y0, **kw), o, case, "launch shape %r" % (kw,))
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+def test_attempts_outside_the_fast_path_range_are_repeated_with_the_plain_operators(arith):
+    """The hot loop's right-hand sides use branch-free division / square root and only record that an operand left their
+    range; the lane loop then repeats the attempt with the stage-by-stage fallback to the plain operators.  A mass parameter
+    outside [2^-60, 2^60) fails the range test on every attempt, so every step of these runs takes that path -- plane
+    variant, general planar kernel (out-of-plane members), spatial system -- and must still equal the oracle bit for bit."""
+    mu = 1e-30
+    for method in (F.ERK_DOP853, F.ERK_DOP54):
+        case = K.cr3bp_case(method, 1e-10, arith, norb=0.4, max_events=8)
+        case.sysparams = [mu]
+        y0 = P.cr3bp_ensemble(200, start=3)
+        K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "planar, mu = 1e-30")
+        y0[2] = 1e-3
+        K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "planar general kernel, mu = 1e-30")
+        case = K.halo_case(method, 1e-9, arith)
+        case.sysparams = [mu]
+        y0 = P.perturbed_ensemble(P.HALO_Y0, 150)
+        K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "spatial, mu = 1e-30")
+
+
 def test_host_pipeline_chunks_match_single_chunk_and_oracle():
     """FLINT_MEM_HOST with flint_exec.pipeline = k: the ensemble runs as k chunks of trajectories on two streams (pitched
     H2D / D2H copies of column ranges of the SoA arrays, fixed launch schedule).  Ragged chunk sizes, more chunks than

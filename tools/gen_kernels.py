@@ -387,8 +387,9 @@ def gen_method(E_out, S, M):
     E(" * truncated the step: reference quirk Q6 rebuilds the dense stages with the new h and the old k's).")
     E(" * Out: ks (stage vectors), Ynew (candidate), Ypre (state of stage sint-1, for CheckStiffness),")
     E(" * Err (0 when !estimate).  The evaluation at (X0+h, Ynew) is always made (it is the next F0")
-    E(" * when the step is accepted and costs 1/%d of the attempt when it is not). */" % (P.n_int))
-    E("template <class SYS, bool FMA, bool DENSE, class KS>")
+    E(" * when the step is accepted and costs 1/%d of the attempt when it is not).  HOT: the call comes from the lane loop" % (P.n_int))
+    E(" * of erk_step_kernel (right-hand sides may be inlined and may defer their range check, arith.cuh: rhs_eval). */")
+    E("template <class SYS, bool FMA, bool DENSE, bool HOT, class KS>")
     E("static __device__ __forceinline__ void step(const SYS& sys, double X0, const double (&Y0)[SYS::N], const double (&F0)[SYS::N],")
     E("        double h, double hd, KS& ks, double (&Ynew)[SYS::N], double (&Ypre)[SYS::N], const Tol& tol,")
     E("        bool estimate, double& Err, const double (&C)[FLINT_NCOEF])")
@@ -412,7 +413,7 @@ def gen_method(E_out, S, M):
             E("{   /* %s */" % (("stage %d" % st) if kind == "stage" else "evaluation at (X0+h, Ynew)"))
             E.ind += 1
             emit_iteration_pre(E, P, it, kind, st)
-            E("{ double fv[N]; rhs_eval<SYS, FMA, FLINT_RHS_COPY(%d, %d), !DENSE>(sys, yt, fv); ks.template put<%d>(fv); }" % (it, len(P.its), P.slot[st]))
+            E("{ double fv[N]; rhs_eval<SYS, FMA, FLINT_RHS_COPY(%d, %d), HOT>(sys, yt, fv); ks.template put<%d>(fv); }" % (it, len(P.its), P.slot[st]))
             E.ind -= 1
             E("}")
         if len(P.its) > P.n_int:
