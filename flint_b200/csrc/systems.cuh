@@ -290,8 +290,12 @@ struct SysTwoBody {
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                           /* position */
     __host__ __device__ static constexpr int fsrc(int c) { return c < 3 ? c + 3 : -2 - (c - 3); }
 
-    template <bool FMA>
-    __device__ __forceinline__ void accel(const double (&y)[NIN], double (&f)[NOUT]) const
+    static constexpr bool LAZY_RANGE = true;                      /* see the planar CR3BP system */
+    mutable bool bad = false;
+    template <bool FMA> __device__ __forceinline__ void accel(const double (&y)[NIN], double (&f)[NOUT]) const { accel_impl<FMA, false>(y, f); }
+    template <bool FMA> __device__ __forceinline__ void accel_lazy(const double (&y)[NIN], double (&f)[NOUT]) const { accel_impl<FMA, true>(y, f); }
+    template <bool FMA, bool LAZY>
+    __device__ __forceinline__ void accel_impl(const double (&y)[NIN], double (&f)[NOUT]) const
     {
         double s = __dmul_rn(y[0], y[0])   /* == 0 + x*x: x*x is never -0 */;
         s = madd<FMA>(y[1], y[1], s);
@@ -300,7 +304,8 @@ struct SysTwoBody {
         const double nr = sqrt_nochk(s);
         const double d = (nr * nr) * nr;
         double fac = div_rcp_nochk(-GM, d, rcp_newton(d));
-        if (!ok) fac = twobody_fac_plain(GM, s);
+        if (LAZY) bad = bad | !ok;
+        else if (!ok) fac = twobody_fac_plain(GM, s);
         f[0] = fac * y[0]; f[1] = fac * y[1]; f[2] = fac * y[2];
     }
     template <bool FMA>

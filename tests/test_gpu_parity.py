@@ -355,6 +355,13 @@ def test_attempts_outside_the_fast_path_range_are_repeated_with_the_plain_operat
         case.sysparams = [mu]
         y0 = P.perturbed_ensemble(P.HALO_Y0, 150)
         K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "spatial, mu = 1e-30")
+    # two-body in other units: GM' = GM * L^3 with lengths scaled by L = 2.15e30 is the same orbit with the same period, but
+    # GM' = 4e96 and r^2 = 4e68 are outside the range of the branch-free operators
+    case = K.twobody_case(F.ERK_DOP853, 1e-10, arith, nper=1)
+    L = 2.1544346900318754e30
+    case.sysparams = [P.TBP_GM * L ** 3]
+    y0 = P.perturbed_ensemble(P.TBP_Y0, 120) * L
+    K.compare_batch(case.run_gpu(y0), case.run_oracle(y0), case, "two-body, GM = %g" % case.sysparams[0])
 
 
 def test_host_pipeline_chunks_match_single_chunk_and_oracle():
