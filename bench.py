@@ -34,7 +34,7 @@ N_PER_GPU = 1 << 20
 RTOL = 1e-12
 MAX_EVENTS = 2
 CPU_SAMPLE = 1 << 18          # cpu_baseline leg: ~10 s of CPU work on 16 cores
-REF_STEP_SAMPLE = 1 << 16     # --impl reference: orbits per step
+REF_STEP_SAMPLE = int(os.environ.get("FLINT_BENCH_REF_SAMPLE", 1 << 16))     # --impl reference: orbits per step (the variable is for the CPU test suite)
 
 
 def parse():

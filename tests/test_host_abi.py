@@ -4,6 +4,8 @@ without a CUDA device (there is no CPU fallback).  No kernel is launched here.""
 import ctypes as C
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -182,3 +184,21 @@ def test_user_registered_systems_on_gpu():
     zero-crossing event agrees with scipy's DOP853 (final state and event times to 1e-8)."""
     out = _run_user_system_check()
     assert "OK user Lorenz == oracle Lorenz" in out and "OK user Van der Pol vs scipy" in out
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): stdout is exactly one JSON line with the contract's
+    keys; everything else goes to stderr."""
+    import json
+    env = dict(os.environ, FLINT_BENCH_REF_SAMPLE="1024")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "CR3BP DOP853 orbits/sec" and d["unit"] == "orbits/s" and d["value"] > 0
+    for key in ("n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
