@@ -979,12 +979,25 @@ __global__ void __launch_bounds__(128, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense
     SYS sys;
     sys.load(p.sp);
     for (int s = blockIdx.y; s < nacc; s += gridDim.y) {
-        if (p.dflag[t * p.dense_cap + s] == 0) continue;             /* written by the event code */
+        /* with two warps per sub-partition every DRAM round trip is exposed (ncu: a quarter of all stall samples sat on the
+         * flag test and on the first use of the log): flag and log are requested together, and the next step's lines are
+         * pulled into L2 while this one is computed */
+        const unsigned char flag = p.dflag[t * p.dense_cap + s];     /* 0: written by the event code */
         const double* __restrict__ rec = p.dbip + (t * p.dense_cap + s) * (long)p.dense_rstride;
-        const double X = rec[0], h = rec[1];
+        double lg[2 * N + 2];
+#pragma unroll
+        for (int c = 0; c < 2 * N + 2; ++c) lg[c] = rec[c];
+        if (s + (int)gridDim.y < nacc) {
+            const long sn = t * p.dense_cap + s + gridDim.y;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dbip + sn * (long)p.dense_rstride));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dbip + sn * (long)p.dense_rstride + 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dflag + sn));
+        }
+        if (flag == 0) continue;
+        const double X = lg[0], h = lg[1];
         double Y[N], F0[N], Yn[N], Yp[N], e, B[PS + 1][N];
 #pragma unroll
-        for (int c = 0; c < N; ++c) { Y[c] = rec[2 + c]; F0[c] = rec[2 + N + c]; }
+        for (int c = 0; c < N; ++c) { Y[c] = lg[2 + c]; F0[c] = lg[2 + N + c]; }
         KStore<METHOD, SYS, 0u> ks;
         ks.s = nullptr;
         METHOD::template step<SYS, FMA, true, false>(sys, X, Y, F0, h, h, ks, Yn, Yp, p.tol, false, e, p.coef);
