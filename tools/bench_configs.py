@@ -54,7 +54,7 @@ if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolat
         for sh in range(NSH):
             sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
             y0 = torch.from_numpy(P.cr3bp_ensemble(SH, start=sh * SH)).cuda()
-            ms, r = run(erk, 0.0, y0, xf, reps=1, dense_cap=640, **ikw)
+            ms, r = run(erk, 0.0, y0, xf, reps=2, dense_cap=640, **ikw)      # best of 2: the first call of a process also loads the kernels
             cnt = r["counters"].cpu().numpy().astype(np.int64)
             fl_tot += P.algorithmic_flops(F.ERK_VERNER98R, F.FLINT_SYS_CR3BP_PLANAR, 6, cnt[0].sum(), cnt[1].sum(), cnt[1].sum())
             acc_tot += int(cnt[1].sum())
