@@ -82,7 +82,8 @@ struct SysCR3BPPlanar {
      * 256 x 2: 81.4 / 125.5 / 70.5, 512 x 1 without barrier: 80.9 / 115.8 / 67.6 */
     static constexpr bool INLINE_ACCEL_HOT = true;
     static constexpr int STEP_BLOCK = 512, STEP_MIN_BLOCKS = 1, STEP_BARRIER = 0;   /* a barrier every 4 / 16 / 64 iterations instead of
-                                                                                       none: 131.0 / 133.9 / 133.5 vs 128.5 ms (plane variant) */
+                                                                                       none: 131.0 / 133.9 / 133.5 vs 128.5 ms (plane variant);
+                                                                                       384 threads at 168 registers / 448 at 146: 125.8 / 132.0 vs 121.4 ms */
     static constexpr unsigned ZPLANE = (1u << 2) | (1u << 5);   /* z = vz = 0 is invariant under F and under every event action below */
     __host__ __device__ static constexpr bool zc(int) { return false; }
     __host__ __device__ static constexpr int in_idx(int i) { return i; }                          /* y0 y1 */
