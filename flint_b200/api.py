@@ -71,9 +71,29 @@ class _EventsOut(C.Structure):
     _fields_ = [("cap", C.c_long), ("rec", C.c_void_p), ("count", C.c_void_p)]
 
 
+FLINT_MAX_DEVICES = 16
+FLINT_SHARD_CHUNK = 4096
+
+
 class _Exec(C.Structure):
     _fields_ = [("mem", C.c_int), ("device", C.c_int), ("stream", C.c_void_p), ("async_", C.c_int),
-                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int), ("pipeline", C.c_int)]
+                ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int), ("pipeline", C.c_int),
+                ("round_len", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * FLINT_MAX_DEVICES), ("shard_chunk", C.c_long)]
+
+
+def _exec(mem, device=0, stream=None, async_=0, dense_cap=0, block_threads=0, blocks_per_sm=0, event_mode=0, plane_variant=0,
+          pipeline=0, round_len=0, devices=None, shard_chunk=0):
+    ex = _Exec()
+    ex.mem, ex.device, ex.stream, ex.async_, ex.dense_cap = int(mem), int(device), stream, int(async_), int(dense_cap)
+    ex.block_threads, ex.blocks_per_sm, ex.event_mode, ex.plane_variant = int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant)
+    ex.pipeline, ex.round_len, ex.shard_chunk = int(pipeline), int(round_len), int(shard_chunk)
+    if devices is not None:
+        devices = list(devices)
+        assert len(devices) <= FLINT_MAX_DEVICES
+        ex.n_devices = len(devices)
+        for k, d in enumerate(devices):
+            ex.devices[k] = int(d)
+    return ex
 
 
 LIB_PATH = os.environ.get("FLINT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflint_b200.so")
@@ -115,6 +135,12 @@ def lib():
         L.flint_b200_last_kernel_ms.restype = C.c_double
         L.flint_b200_selftest_arith.restype = C.c_int
         L.flint_b200_selftest_arith.argtypes = [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+        L.flint_b200_shard_count.restype = C.c_long
+        L.flint_b200_shard_count.argtypes = [C.c_long, C.c_int, C.c_int, C.c_long]
+        L.flint_b200_shard_global_index.restype = C.c_long
+        L.flint_b200_shard_global_index.argtypes = [C.c_long, C.c_int, C.c_int, C.c_long, C.c_long]
+        L.flint_b200_shard_indices.restype = C.c_long
+        L.flint_b200_shard_indices.argtypes = [C.c_long, C.c_int, C.c_int, C.c_long, C.c_void_p]
         _lib = L
     return _lib
 
@@ -309,11 +335,12 @@ class ERK:
     def IntegrateBatch(self, X0, Y0, Xf, StepSz=None, UseConstStepSz=None, StepAdvance=None, IntStepsOn=None,
                        EventMask=None, EventStates=False, StiffTest=None, params=None, MaxEvents=4, StepsCap=None,
                        out=None, device=0, stream=None, dense_cap=0, block_threads=0, blocks_per_sm=0, want_counters=True,
-                       event_mode=0, plane_variant=0, async_=False, pipeline=0):
+                       event_mode=0, plane_variant=0, async_=False, pipeline=0, round_len=0, devices=None, shard_chunk=0):
         """Y0: (n, N) structure-of-arrays, numpy (host buffers: the call stages H2D/D2H itself) or a
         torch CUDA tensor (device buffers: nothing is copied).  Xf scalar or (N,).  Returns a dict of
         SoA outputs (numpy or torch, matching the input kind).  async_ (device buffers only): return after enqueueing
-        on the stream; the caller synchronises before reading the outputs."""
+        on the stream; the caller synchronises before reading the outputs.  devices=[d0, d1, ..] (host buffers): the ensemble
+        is sharded over these GPUs inside the call (block-cyclic chunks of shard_chunk trajectories); round_len: see flint_exec."""
         n = self.sys.n
         keep = []
         io = self._int_opts(UseConstStepSz, StepAdvance, IntStepsOn, EventMask, params, keep)
@@ -368,8 +395,8 @@ class ERK:
             ecount = out.get("nEvents") if out.get("nEvents") is not None else zeros((N,), i32)
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
-        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, int(bool(async_) and on_dev), int(dense_cap),
-                   int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant), int(pipeline))
+        ex = _exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, device, stream, int(bool(async_) and on_dev), dense_cap,
+                   block_threads, blocks_per_sm, event_mode, plane_variant, pipeline, round_len, devices, shard_chunk)
         x0s = float(X0) if x0v is None else 0.0
         st = lib().flint_erk_integrate_batch(self._h, N, x0s, _ptr(x0v), _ptr(Y0), _ptr(xf), _ptr(yf), _ptr(h), C.byref(io),
                                              _ptr(counters), _ptr(status), C.byref(steps) if steps else None,
@@ -406,7 +433,7 @@ class ERK:
             Xarr = np.ascontiguousarray(np.asarray(Xarr, dtype=np.float64))
             yarr = out if out is not None else np.empty(shape)
             status = np.zeros((N,), dtype=np.int32)
-        ex = _Exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, int(device), stream, 0, 0, 0, 0, 0, 0, 0)
+        ex = _exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, device, stream)
         st = lib().flint_erk_interpolate_batch(self._h, _ptr(Xarr), G, _ptr(yarr), int(layout), _ptr(status),
                                                int(SaveInterpCoeffs is not None), int(bool(SaveInterpCoeffs)), C.byref(ex))
         self.status = st
@@ -444,3 +471,17 @@ def selftest_arith(n=1 << 26, seed=12345):
 
 def launch_count():
     return int(lib().flint_b200_launch_count())
+
+
+def shard_count(N, n_shards, shard, chunk=FLINT_SHARD_CHUNK):
+    """Trajectories of `shard` in the block-cyclic deal of [0, N) over n_shards (devices of a call / ranks of a job)."""
+    return int(lib().flint_b200_shard_count(int(N), int(n_shards), int(shard), int(chunk)))
+
+
+def shard_indices(N, n_shards, shard, chunk=FLINT_SHARD_CHUNK):
+    """Global trajectory indices of `shard`, in the shard's local order (int64 array)."""
+    cnt = shard_count(N, n_shards, shard, chunk)
+    out = np.empty(cnt, dtype=np.int64)
+    got = lib().flint_b200_shard_indices(int(N), int(n_shards), int(shard), int(chunk), out.ctypes.data)
+    assert got == cnt
+    return out

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -22,8 +24,8 @@
 using flint::KArgs;
 
 static thread_local std::string g_last_error;
-static long g_launches = 0;
-static double g_last_kernel_ms = 0.0;
+static std::atomic<long> g_launches{0};                 /* handles on different devices launch from different host threads */
+static std::atomic<double> g_last_kernel_ms{0.0};
 
 static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 static bool cuda_ok(cudaError_t e, const char* what)
@@ -100,6 +102,13 @@ struct flint_erk {
     int pipe_device = -1;
     bool dense_is_scalar = false;
     bool dense_allocated = false;      /* allocated(me%Xint) */
+    double last_kernel_ms = 0.0;       /* device time of the last batch Integrate of this handle (CUDA events on its stream) */
+    unsigned long long* pinned = nullptr;   /* page-locked words the kernels' counters are read back into */
+    /* one sub-handle per device of a sharded call (flint_exec.n_devices > 1): same options, own stream / workspace / dense store */
+    std::vector<flint_erk*> shard;
+    std::vector<cudaStream_t> shard_stream;
+    std::vector<int> shard_device;
+    long shard_N = 0, shard_chunk = 0;      /* the partition of the last sharded Integrate (Interpolate follows it) */
 };
 
 /* ------------------------------------------------------------------ misc */
@@ -113,8 +122,8 @@ static const char* const kErrorStrings[17] = {   /* src/FLINT_base.f90:64-82 */
 
 extern "C" const char* flint_status_string(int s) { return (s >= 0 && s <= 16) ? kErrorStrings[s] : kErrorStrings[3]; }
 extern "C" const char* flint_last_error(void) { return g_last_error.c_str(); }
-extern "C" long flint_b200_launch_count(void) { return g_launches; }
-extern "C" double flint_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+extern "C" long flint_b200_launch_count(void) { return g_launches.load(); }
+extern "C" double flint_b200_last_kernel_ms(void) { return g_last_kernel_ms.load(); }
 extern "C" int flint_b200_device_count(void)
 {
     int n = 0;
@@ -172,6 +181,12 @@ extern "C" flint_erk_t* flint_erk_create(void) { return new flint_erk(); }
 extern "C" void flint_erk_destroy(flint_erk_t* e)
 {
     if (!e) return;
+    for (size_t k = 0; k < e->shard.size(); ++k) {
+        if (e->shard_stream[k]) { cudaSetDevice(e->shard_device[k]); cudaStreamDestroy(e->shard_stream[k]); }
+        flint_erk_destroy(e->shard[k]);
+    }
+    e->shard.clear();
+    if (e->pinned) cudaFreeHost(e->pinned);
     e->dense.release();
     for (int k = 0; k < 2; ++k) { e->stage_int[k].release(); e->ws[k].release(); if (e->pipe_stream[k]) cudaStreamDestroy(e->pipe_stream[k]); e->pipe_stream[k] = nullptr; }
     delete e;
@@ -261,6 +276,34 @@ extern "C" int flint_erk_init(flint_erk_t* me, const flint_sys_t* DE, int max_st
     return me->status;
 }
 
+/* ------------------------------------------------------------------ partition of an ensemble over shards */
+static long shard_count(long N, int D, int d, long chunk)
+{
+    if (N <= 0 || D < 1 || d < 0 || d >= D) return 0;
+    if (chunk <= 0) chunk = FLINT_SHARD_CHUNK;
+    const long nch = (N + chunk - 1) / chunk;               /* chunks c = d, d + D, ... < nch; only chunk nch-1 may be short */
+    if (d >= nch) return 0;
+    const long mine = (nch - 1 - d) / D + 1;
+    long cnt = mine * chunk;
+    if ((nch - 1) % D == d) cnt -= nch * chunk - N;
+    return cnt;
+}
+static long shard_global(long N, int D, int d, long chunk, long i)
+{
+    if (chunk <= 0) chunk = FLINT_SHARD_CHUNK;
+    if (i < 0 || i >= shard_count(N, D, d, chunk)) return -1;
+    return ((i / chunk) * D + d) * chunk + i % chunk;
+}
+extern "C" long flint_b200_shard_count(long N, int n_shards, int shard, long chunk) { return shard_count(N, n_shards, shard, chunk); }
+extern "C" long flint_b200_shard_global_index(long N, int n_shards, int shard, long chunk, long i) { return shard_global(N, n_shards, shard, chunk, i); }
+extern "C" long flint_b200_shard_indices(long N, int n_shards, int shard, long chunk, long* out)
+{
+    const long cnt = shard_count(N, n_shards, shard, chunk);
+    if (chunk <= 0) chunk = FLINT_SHARD_CHUNK;
+    if (out) for (long i = 0; i < cnt; ++i) out[i] = ((i / chunk) * n_shards + shard) * chunk + i % chunk;
+    return cnt;
+}
+
 /* ------------------------------------------------------------------ Integrate */
 namespace {
 
@@ -287,15 +330,66 @@ struct DevBuf {
 
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
-    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0, round_len = 0;
+    int n_devices = 0; int devices[FLINT_MAX_DEVICES] = {0}; long shard_chunk = 0;
+};
+
+/* Which columns of the caller's SoA host arrays (row pitch Ntot) a call works on: shard d of D in the block-cyclic deal of
+ * `chunk` trajectories (include/flint_b200.h: flint_b200_shard_*).  D == 1: all of them, in order. */
+struct Shard {
+    long Ntot = 0; int D = 1, d = 0; long chunk = FLINT_SHARD_CHUNK;
 };
 
 }  // namespace
 
+/* rows x cnt elements between a compact device array [rows][cnt] and the shard's columns of a host array of row pitch Ntot:
+ * columns [off, off+cnt) of an unsharded call; the shard's chunks (one strided 2-D copy per row, or one for all rows when the
+ * rows line up with the deal) of a sharded one.  N = the call's local trajectory count. */
+static bool shard_copy(const Shard& sh, long N, long off, long cnt, void* dst, const void* src, size_t elem, size_t rows,
+                       bool to_device, const char* what, cudaStream_t s)
+{
+    const size_t szN = (size_t)cnt, szT = (size_t)sh.Ntot;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (sh.D == 1) {
+        if (cnt == N && (size_t)N == szT) return cuda_ok(cudaMemcpyAsync(dst, src, rows * szN * elem, kind, s), what);
+        if (to_device)
+            return cuda_ok(cudaMemcpy2DAsync(dst, szN * elem, (const char*)src + (size_t)off * elem, szT * elem, szN * elem, rows, kind, s), what);
+        return cuda_ok(cudaMemcpy2DAsync((char*)dst + (size_t)off * elem, szT * elem, src, szN * elem, szN * elem, rows, kind, s), what);
+    }
+    /* sharded: local trajectory i = k * chunk + r is global ((k * D + d) * chunk + r); off == 0, cnt == N (no pipeline) */
+    char* hbase = to_device ? (char*)src : (char*)dst;       /* host side */
+    char* dbase = to_device ? (char*)dst : (char*)src;       /* device side, compact [rows][cnt] */
+    const size_t ch = (size_t)sh.chunk, K = szN / ch, tail = szN % ch, stride = (size_t)sh.D * ch;
+    bool ok = true;
+    auto one = [&](char* h, size_t hpitch, char* d, size_t dpitch, size_t width, size_t height) {
+        if (!ok || width == 0 || height == 0) return;
+        if (height == 1 || hpitch > (size_t)1 << 30) {       /* plain copies: no pitch limit (a "column" may be a whole trajectory's Yarr) */
+            for (size_t r = 0; r < height && ok; ++r)
+                ok = to_device ? cuda_ok(cudaMemcpyAsync(d + r * dpitch, h + r * hpitch, width, kind, s), what)
+                               : cuda_ok(cudaMemcpyAsync(h + r * hpitch, d + r * dpitch, width, kind, s), what);
+            return;
+        }
+        ok = to_device ? cuda_ok(cudaMemcpy2DAsync(d, dpitch, h, hpitch, width, height, kind, s), what)
+                       : cuda_ok(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, height, kind, s), what);
+    };
+    if (tail == 0 && szT % stride == 0 && szT / stride == K) {
+        /* every row holds exactly K chunks of this shard, one deal period apart: rows * K lines of one copy */
+        one(hbase + (size_t)sh.d * ch * elem, stride * elem, dbase, ch * elem, ch * elem, rows * K);
+        return ok;
+    }
+    for (size_t r = 0; r < rows && ok; ++r) {
+        char* hrow = hbase + (r * szT + (size_t)sh.d * ch) * elem;
+        char* drow = dbase + r * szN * elem;
+        one(hrow, stride * elem, drow, ch * elem, ch * elem, K);
+        if (tail) one(hrow + K * stride * elem, tail * elem, drow + K * ch * elem, tail * elem, tail * elem, 1);
+    }
+    return ok;
+}
+
 static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double* x0, const double* y0, double* xf,
                           double* yf, double* stepsz, const flint_int_opts* io, int* counters, int* status,
                           flint_steps_out* steps, flint_events_out* events, int* stifftest, const ExecCtx& ex,
-                          bool scalar_call)
+                          bool scalar_call, const Shard* shard_in = nullptr)
 {
     if (!me->inited || !me->sys) return me->status = FLINT_ERROR_INIT_REQD;
     const flint_sys& sys = *me->sys;
@@ -323,8 +417,12 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         if (evmask == 0) events_on = false;
         else if (!events || !events->rec || !events->count) return me->status = FLINT_ERROR_EVENTPARAMS;
     }
+    if ((io->present & FLINT_INT_PARAMS) && (io->n_params < 0 || io->n_params > 8 || (io->n_params > 0 && !io->params)))
+        return me->status = fail(FLINT_ERROR_PARAMS, "params(:): at most 8 values are forwarded to the device functors");
     if (st != FLINT_SUCCESS) return me->status = st;                                          /* :196-199 */
     if (N <= 0) return me->status = FLINT_SUCCESS;
+    Shard sh;
+    if (shard_in) sh = *shard_in; else sh.Ntot = N;
 
     if (!cuda_ok(cudaSetDevice(ex.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const bool dense = me->interp_on;
@@ -356,6 +454,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     a.steps_cap = int_steps ? steps->cap : 0;
     a.ev_cap = events_on ? events->cap : 0;
     a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
+    a.round_req = ex.round_len;
+    if (io->present & FLINT_INT_PARAMS) { a.n_params = io->n_params; for (int i = 0; i < io->n_params; ++i) a.params[i] = io->params[i]; }
 
     ke->load_coefficients(a.coef);
     flint::det_pow_constants(a.powc);
@@ -388,7 +488,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
      * 2^20 orbits) every chunk adds the tails of its two step passes and the call gets slower -- measured, 2^20 orbits:
      * 151 ms (1 chunk), 152 (2), 162 (4), 182 (8); profiles/r01_notes.md. ---- */
     long n_chunks = 1;
-    if (ex.host && !dense && !int_steps && !scalar_call && ex.pipeline != 1) {
+    if (ex.host && !dense && !int_steps && !scalar_call && ex.pipeline != 1 && sh.D == 1) {
         n_chunks = ex.pipeline >= 2 ? ex.pipeline : 1;
         if (const char* e = getenv("FLINT_B200_PIPE_CHUNKS")) { const long v = atol(e); if (v >= 1) n_chunks = v; }
         if (n_chunks > N) n_chunks = N;
@@ -407,25 +507,18 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 return me->status = FLINT_ERROR;
         me->pipe_device = ex.device;
     }
-    const size_t szT = (size_t)N;                                  /* row pitch (elements) of the caller's SoA arrays */
+    const size_t szT = (size_t)sh.Ntot;                            /* row pitch (elements) of the caller's SoA arrays */
+    if (!me->pinned && !cuda_ok(cudaHostAlloc((void**)&me->pinned, 64, cudaHostAllocDefault), "cudaHostAlloc")) return me->status = FLINT_ERROR;
 
     /* one chunk [off, off + cnt) of the ensemble on stream s with the buffers of pipeline slot `slot` */
     auto run_chunk = [&](long off, long cnt, int slot, cudaStream_t s, bool fixed_schedule, cudaEvent_t e0, cudaEvent_t e1) -> int {
         KArgs c = a;
         c.N = cnt;
         const size_t szN = (size_t)cnt;
-        int* ev_snap = nullptr;                     /* event counts at the time of the early copy */
-        bool early_done = false;
+        bool early_done = false, reparked = false;  /* early copy of the event records issued / a trajectory parked again after it */
         cudaEvent_t ev_ready = nullptr;
-        /* rows x cnt elements between a compact device array and columns [off, off+cnt) of a host array of pitch N */
-        auto copy2d = [&](void* dst, const void* src, size_t elem, size_t rows, bool to_device, const char* what) -> bool {
-            if (cnt == N)
-                return cuda_ok(cudaMemcpyAsync(dst, src, rows * szN * elem, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s), what);
-            if (to_device)
-                return cuda_ok(cudaMemcpy2DAsync(dst, szN * elem, (const char*)src + (size_t)off * elem, szT * elem, szN * elem, rows,
-                                                 cudaMemcpyHostToDevice, s), what);
-            return cuda_ok(cudaMemcpy2DAsync((char*)dst + (size_t)off * elem, szT * elem, src, szN * elem, szN * elem, rows,
-                                             cudaMemcpyDeviceToHost, s), what);
+        auto copy2d = [&](void* dst, const void* src, size_t elem, size_t rows, bool to_device, const char* what, cudaStream_t st) -> bool {
+            return shard_copy(sh, N, off, cnt, dst, src, elem, rows, to_device, what, st);
         };
         /* ---- device views of the caller's buffers ---- */
         if (ex.host) {
@@ -435,19 +528,18 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             double* d_yf = scratch.alloc<double>(szN * n);
             int* d_status = scratch.alloc<int>(szN);
             if (!d_y0 || !d_xf || !d_yf || !d_status) return fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
-            bool ok = copy2d(d_y0, y0, 8, n, true, "H2D y0") && copy2d(d_xf, xf, 8, 1, true, "H2D xf");
+            bool ok = copy2d(d_y0, y0, 8, n, true, "H2D y0", s) && copy2d(d_xf, xf, 8, 1, true, "H2D xf", s);
             c.y0 = d_y0; c.xf = d_xf; c.yf = d_yf; c.status = d_status;
-            if (x0) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, x0, 8, 1, true, "H2D x0"); c.x0 = d; }
-            if (stepsz) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, stepsz, 8, 1, true, "H2D stepsz"); c.stepsz = d; }
+            if (x0) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, x0, 8, 1, true, "H2D x0", s); c.x0 = d; }
+            if (stepsz) { double* d = scratch.alloc<double>(szN); ok = ok && d && copy2d(d, stepsz, 8, 1, true, "H2D stepsz", s); c.stepsz = d; }
             if (counters) { c.counters = scratch.alloc<int>(szN * 4); ok = ok && c.counters; }
-            if (stifftest) { int* d = scratch.alloc<int>(szN); ok = ok && d && copy2d(d, stifftest, 4, 1, true, "H2D stifftest"); c.stifftest = d; }
+            if (stifftest) { int* d = scratch.alloc<int>(szN); ok = ok && d && copy2d(d, stifftest, 4, 1, true, "H2D stifftest", s); c.stifftest = d; }
             if (events_on) {
                 c.ev_count = scratch.alloc<int>(szN);
                 c.ev_rec = scratch.alloc<double>(szN * (size_t)(n + 2) * (size_t)c.ev_cap);
                 ok = ok && c.ev_count && c.ev_rec;
                 /* slots the run does not fill read back as NaN (all-ones pattern) */
                 ok = ok && cuda_ok(cudaMemsetAsync(c.ev_rec, 0xFF, szN * (size_t)(n + 2) * (size_t)c.ev_cap * 8, s), "memset ev_rec");
-                if (early_ev) { ev_snap = scratch.alloc<int>(szN); ok = ok && ev_snap; }
             }
             if (int_steps) {
                 c.xint = scratch.alloc<double>(szN * (size_t)c.steps_cap);
@@ -506,8 +598,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
          * erk_init_kernel.  Set on the device: a pageable H2D copy would make the host wait for everything queued on this stream */
         if (!cuda_ok(flint::launch_set_counters(ctr, 0ULL, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
         g_launches += 1;
-        if (early_ev && !cuda_ok(cudaMemsetAsync(ctr + 4, 0, 8, s), "memset flag")) return FLINT_ERROR;   /* [4]: event counts changed after the early copy */
         c.work_counter = ctr;
+        c.n_items_exact = 1;                                   /* pass 0 runs all cnt trajectories (gang-scheduled kernel, erk_kernel.cuh) */
         c.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
         const int grid_all = (int)((cnt + 127) / 128);
 
@@ -530,23 +622,24 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
                 long n_parked = cnt;
                 if (!fixed_schedule) {
-                    unsigned long long cc = 0;
-                    if (!cuda_ok(cudaMemcpyAsync(&cc, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
+                    /* the parked count through a page-locked word: a pageable destination would be staged by the driver */
+                    if (!cuda_ok(cudaMemcpyAsync(me->pinned, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
                         !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
-                    n_parked = (long)cc;
+                    n_parked = (long)me->pinned[0];
                     if (n_parked == 0) break;
+                    if (round >= 1) reparked = true;           /* events located after the early copy of the records */
                 }
                 int* lcur = cur == 1 ? listA : listB;
                 int* loth = cur == 1 ? listB : listA;
                 const int oth = cur == 1 ? 2 : 1;
                 c.list_in = lcur; c.n_in = ctr + cur; c.list_out = loth; c.n_out = ctr + oth;
+                c.n_items_exact = fixed_schedule ? 0 : 1;      /* synchronous calls know every pass's item count */
                 le = ke->event(c, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
                 g_launches += 1;
                 if (le != cudaSuccess) break;
                 bool issue_early = false;
-                if (early_ev && round == 0 && ev_snap) {       /* stream order: snapshot and marker before the resume pass */
-                    const bool ok = cuda_ok(cudaMemcpyAsync(ev_snap, c.ev_count, szN * 4, cudaMemcpyDeviceToDevice, s), "snapshot of the event counts") &&
-                                    cuda_ok(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming), "cudaEventCreate") &&
+                if (early_ev && round == 0) {                  /* stream order: the marker sits between the event kernel and the resume pass */
+                    const bool ok = cuda_ok(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming), "cudaEventCreate") &&
                                     cuda_ok(cudaEventRecord(ev_ready, s), "cudaEventRecord");
                     if (!ok) { le = cudaErrorUnknown; break; }
                     issue_early = true;
@@ -561,9 +654,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 if (issue_early && le == cudaSuccess) {        /* issued after the launch: a pageable destination blocks the host, not the GPU */
                     cudaStream_t s2 = me->pipe_stream[1];
                     const bool ok = cuda_ok(cudaStreamWaitEvent(s2, ev_ready, 0), "cudaStreamWaitEvent") &&
-                                    cuda_ok(cudaMemcpyAsync(events->count, ev_snap, szN * 4, cudaMemcpyDeviceToHost, s2), "early D2H ev_count") &&
-                                    cuda_ok(cudaMemcpyAsync(events->rec, c.ev_rec, szN * (size_t)(n + 2) * (size_t)c.ev_cap * 8, cudaMemcpyDeviceToHost, s2),
-                                            "early D2H ev_rec");
+                                    copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "early D2H ev_rec", s2);
                     if (!ok) { le = cudaErrorUnknown; break; }
                     early_done = true;
                 }
@@ -579,30 +670,23 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         if (!cuda_ok(le, "kernel launch")) { if (ev_ready) cudaEventDestroy(ev_ready); return FLINT_ERROR; }
 
         if (ex.host) {
-            bool ok = copy2d(xf, c.xf, 8, 1, false, "D2H xf") && copy2d(yf, c.yf, 8, n, false, "D2H yf");
-            if (status) ok = ok && copy2d(status, c.status, 4, 1, false, "D2H status");
-            if (stepsz && !const_step) ok = ok && copy2d(stepsz, c.stepsz, 8, 1, false, "D2H stepsz");
-            if (counters) ok = ok && copy2d(counters, c.counters, 4, 4, false, "D2H counters");
-            if (stifftest) ok = ok && copy2d(stifftest, c.stifftest, 4, 1, false, "D2H stifftest");
-            if (events_on && !early_done)
-                ok = ok && copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count") &&
-                     copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec");
+            bool ok = copy2d(xf, c.xf, 8, 1, false, "D2H xf", s) && copy2d(yf, c.yf, 8, n, false, "D2H yf", s);
+            if (status) ok = ok && copy2d(status, c.status, 4, 1, false, "D2H status", s);
+            if (stepsz && !const_step) ok = ok && copy2d(stepsz, c.stepsz, 8, 1, false, "D2H stepsz", s);
+            if (counters) ok = ok && copy2d(counters, c.counters, 4, 4, false, "D2H counters", s);
+            if (stifftest) ok = ok && copy2d(stifftest, c.stifftest, 4, 1, false, "D2H stifftest", s);
+            /* the counts are final only now (a trajectory writes its count when it finishes); the records went out during
+             * the resume pass and are complete unless a trajectory parked again after that copy */
+            if (events_on) ok = ok && copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count", s);
+            if (events_on && !early_done) ok = ok && copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec", s);
             if (int_steps) {
-                ok = ok && copy2d(steps->xint, c.xint, 8, (size_t)c.steps_cap, false, "D2H xint") &&
-                     copy2d(steps->yint, c.yint, 8, (size_t)c.steps_cap * n, false, "D2H yint");
-                if (steps->count) ok = ok && copy2d(steps->count, c.steps_count, 4, 1, false, "D2H steps_count");
+                ok = ok && copy2d(steps->xint, c.xint, 8, (size_t)c.steps_cap, false, "D2H xint", s) &&
+                     copy2d(steps->yint, c.yint, 8, (size_t)c.steps_cap * n, false, "D2H yint", s);
+                if (steps->count) ok = ok && copy2d(steps->count, c.steps_count, 4, 1, false, "D2H steps_count", s);
             }
             if (ok && early_done) {
-                /* did any trajectory record another event after the early copy?  then the records travel again */
-                unsigned long long changed = 0;
-                ok = cuda_ok(flint::launch_any_differs(c.ev_count, ev_snap, cnt, ctr + 4, s), "event count check") &&
-                     cuda_ok(cudaMemcpyAsync(&changed, ctr + 4, 8, cudaMemcpyDeviceToHost, s), "D2H event flag") &&
-                     cuda_ok(cudaStreamSynchronize(s), "kernel execution") &&
-                     cuda_ok(cudaStreamSynchronize(me->pipe_stream[1]), "early event copy");
-                g_launches += 1;
-                if (ok && changed)
-                    ok = copy2d(events->count, c.ev_count, 4, 1, false, "D2H ev_count") &&
-                         copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec");
+                ok = cuda_ok(cudaStreamSynchronize(me->pipe_stream[1]), "early event copy");     /* never two copies into the same host lines */
+                if (ok && reparked) ok = copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "D2H ev_rec", s);
             }
             if (ev_ready) cudaEventDestroy(ev_ready);
             if (!ok) return FLINT_ERROR;
@@ -646,6 +730,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     if (timed) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
+        me->last_kernel_ms = ms;
         g_last_kernel_ms = ms;
         drop_events();
     }
@@ -658,9 +743,55 @@ static ExecCtx make_exec(const flint_exec* x)
     if (x) {
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
-        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline;
+        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline; e.round_len = x->round_len;
+        e.n_devices = x->n_devices; e.shard_chunk = x->shard_chunk > 0 ? x->shard_chunk : FLINT_SHARD_CHUNK;
+        for (int k = 0; k < FLINT_MAX_DEVICES; ++k) e.devices[k] = x->devices[k];
     }
     return e;
+}
+
+/* Init's results copied into the sub-handle of one device of a sharded call */
+static void sync_options(flint_erk* dst, const flint_erk* src)
+{
+    dst->status = src->status; dst->inited = src->inited;
+    dst->sys_copy = src->sys_copy; dst->sys = src->sys ? &dst->sys_copy : nullptr;
+    dst->method = src->method; dst->max_steps = src->max_steps; dst->scalar_tol = src->scalar_tol;
+    for (int i = 0; i < FLINT_MAX_N; ++i) { dst->atol[i] = src->atol[i]; dst->rtol[i] = src->rtol[i]; dst->istates[i] = src->istates[i]; }
+    dst->interp_on = src->interp_on; dst->nI = src->nI; dst->min_step = src->min_step; dst->max_step = src->max_step;
+    for (int i = 0; i < 6; ++i) dst->szp[i] = src->szp[i];
+    dst->events_on = src->events_on;
+    for (int i = 0; i < FLINT_MAX_M; ++i) { dst->ev_stepsz[i] = src->ev_stepsz[i]; dst->ev_opt[i] = src->ev_opt[i]; dst->etol[i] = src->etol[i]; }
+    dst->arith = src->arith; dst->s = src->s; dst->sint = src->sint; dst->p = src->p; dst->q = src->q; dst->pstar = src->pstar;
+    dst->dense_allocated = src->dense_allocated;
+}
+
+/* The sub-handles and streams of a sharded call, created on first use and kept (staging buffers, workspaces, dense stores) */
+static int prepare_shards(flint_erk* me, const ExecCtx& ex)
+{
+    const int D = ex.n_devices;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+    for (int k = 0; k < D; ++k) {
+        /* a device may be listed more than once: its shards then share the GPU (two streams); the tests of a one-GPU box do that */
+        if (ex.devices[k] < 0 || ex.devices[k] >= ndev) return fail(FLINT_ERROR_PARAMS, "flint_exec.devices: no such CUDA device");
+    }
+    bool same = (int)me->shard.size() == D;
+    for (int k = 0; same && k < D; ++k) same = me->shard_device[k] == ex.devices[k];
+    if (!same) {
+        for (size_t k = 0; k < me->shard.size(); ++k) {
+            if (me->shard_stream[k]) { cudaSetDevice(me->shard_device[k]); cudaStreamDestroy(me->shard_stream[k]); }
+            flint_erk_destroy(me->shard[k]);
+        }
+        me->shard.clear(); me->shard_stream.clear(); me->shard_device.clear();
+        for (int k = 0; k < D; ++k) {
+            cudaStream_t st = nullptr;
+            if (!cuda_ok(cudaSetDevice(ex.devices[k]), "cudaSetDevice") ||
+                !cuda_ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return FLINT_ERROR;
+            me->shard.push_back(new flint_erk()); me->shard_stream.push_back(st); me->shard_device.push_back(ex.devices[k]);
+        }
+    }
+    for (int k = 0; k < D; ++k) sync_options(me->shard[k], me);
+    return FLINT_SUCCESS;
 }
 
 extern "C" int flint_erk_integrate_batch(flint_erk_t* me, long N, double x0_scalar, const double* x0, const double* y0,
@@ -670,7 +801,47 @@ extern "C" int flint_erk_integrate_batch(flint_erk_t* me, long N, double x0_scal
 {
     if (!me) return FLINT_ERROR_PARAMS;
     if (!y0 || !xf || !yf) return me->status = fail(FLINT_ERROR_PARAMS, "y0, xf and yf are required");
-    return integrate_impl(me, N, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest, make_exec(exec), false);
+    const ExecCtx ex = make_exec(exec);
+    if (ex.n_devices <= 1) {
+        ExecCtx e1 = ex;
+        if (ex.n_devices == 1) e1.device = ex.devices[0];
+        me->shard_N = 0;
+        return integrate_impl(me, N, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest, e1, false);
+    }
+    /* ---- the ensemble sharded over the devices of one box: chunks of shard_chunk trajectories dealt round-robin;
+     * one host thread, one stream, one set of staging buffers per device; every trajectory is independent, so there is no
+     * exchange step and nothing to reduce -- results are copied to the caller's arrays at the trajectories' own offsets ---- */
+    if (!ex.host) return me->status = fail(FLINT_ERROR_PARAMS, "a sharded call takes host buffers (FLINT_MEM_HOST)");
+    if (ex.n_devices > FLINT_MAX_DEVICES) return me->status = fail(FLINT_ERROR_PARAMS, "flint_exec.n_devices > FLINT_MAX_DEVICES");
+    if (!me->inited || !me->sys) return me->status = FLINT_ERROR_INIT_REQD;
+    if (N <= 0) return me->status = FLINT_SUCCESS;
+    { const int rc = prepare_shards(me, ex); if (rc != FLINT_SUCCESS) return me->status = rc; }
+    const int D = ex.n_devices;
+    std::vector<int> rc(D, FLINT_SUCCESS);
+    std::vector<std::string> err(D);
+    std::vector<std::thread> th;
+    for (int k = 0; k < D; ++k) {
+        th.emplace_back([&, k]() {
+            Shard sh; sh.Ntot = N; sh.D = D; sh.d = k; sh.chunk = ex.shard_chunk;
+            ExecCtx e1 = ex;
+            e1.device = ex.devices[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0; e1.pipeline = 1;
+            const long nk = shard_count(N, D, k, sh.chunk);
+            rc[k] = integrate_impl(me->shard[k], nk, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest,
+                                   e1, false, &sh);
+            if (rc[k] != FLINT_SUCCESS) err[k] = g_last_error;
+        });
+    }
+    for (auto& t : th) t.join();
+    double ms = 0.0;
+    int st = FLINT_SUCCESS;
+    for (int k = 0; k < D; ++k) {
+        if (me->shard[k]->last_kernel_ms > ms) ms = me->shard[k]->last_kernel_ms;
+        if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
+    }
+    me->last_kernel_ms = ms; g_last_kernel_ms = ms;            /* the call's device time: the slowest shard */
+    me->shard_N = N; me->shard_chunk = ex.shard_chunk;
+    me->dense.release();                                       /* the dense output of this call lives in the shards */
+    return me->status = st;
 }
 
 extern "C" int flint_erk_integrate(flint_erk_t* me, double x0, const double* y0, double* xf, double* yf, double* stepsz,
@@ -713,16 +884,20 @@ extern "C" int flint_erk_integrate(flint_erk_t* me, double x0, const double* y0,
 
 /* ------------------------------------------------------------------ Interpolate */
 static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* yarr, int layout, int* status,
-                            bool has_save, bool save, const ExecCtx& ex, bool scalar_call)
+                            bool has_save, bool save, const ExecCtx& ex, bool scalar_call, const Shard* shard_in = nullptr)
 {
     if (!me->interp_on) return me->status = FLINT_ERROR_INTP_OFF;                       /* src/ERKInterp.f90:45-48 */
     const bool dealloc = has_save ? !save : true;                                        /* :52-53 */
     if (G < 1) return me->status;                                                        /* :56-57 */
     DenseStore& D = me->dense;
     if (!D.dxint || D.N <= 0) return me->status = FLINT_ERROR_INTP_OFF;                  /* storage already freed */
+    if (scalar_call && !(me->dense_is_scalar && D.N == 1))     /* the scalar Interpolate reads the dense output of a scalar Integrate */
+        return me->status = fail(FLINT_ERROR_INTP_OFF, "flint_erk_interpolate: the stored dense output belongs to a batch Integrate; use flint_erk_interpolate_batch");
     if (!xarr || !yarr) return me->status = fail(FLINT_ERROR_PARAMS, "xarr and yarr are required");
     if (!cuda_ok(cudaSetDevice(D.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const long N = D.N;
+    Shard sh;
+    if (shard_in) sh = *shard_in; else sh.Ntot = N;
     cudaStream_t s = ex.stream;
     ScopedCache scoped;                      /* Yarr can be most of the device memory: not kept between calls */
     DevBuf scratch(scoped, D.device);
@@ -754,14 +929,19 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     std::vector<int> hst;
     if (ex.host) {
         hst.resize((size_t)N);
-        if (!cuda_ok(cudaMemcpyAsync(hst.data(), d_st, (size_t)N * 4, cudaMemcpyDeviceToHost, s), "D2H status") ||
-            !cuda_ok(cudaMemcpyAsync(yarr, d_y, ny * 8, cudaMemcpyDeviceToHost, s), "D2H yarr"))
-            return me->status = FLINT_ERROR;
+        /* layout 0: a trajectory's Yarr(nI,G) is one "element" of a one-row array; layout 1: nI*G rows of N doubles */
+        const bool okc = cuda_ok(cudaMemcpyAsync(hst.data(), d_st, (size_t)N * 4, cudaMemcpyDeviceToHost, s), "D2H status") &&
+                         (layout == 0 ? shard_copy(sh, N, 0, N, yarr, d_y, (size_t)G * (size_t)D.nI * 8, 1, false, "D2H yarr", s)
+                                      : shard_copy(sh, N, 0, N, yarr, d_y, 8, (size_t)G * (size_t)D.nI, false, "D2H yarr", s));
+        if (!okc) return me->status = FLINT_ERROR;
     }
     if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;
     int rc = me->status;
     if (ex.host) {
-        if (status) for (long i = 0; i < N; ++i) status[i] = hst[(size_t)i];
+        if (status) {
+            if (sh.D == 1) for (long i = 0; i < N; ++i) status[i] = hst[(size_t)i];
+            else for (long i = 0; i < N; ++i) status[((i / sh.chunk) * sh.D + sh.d) * sh.chunk + i % sh.chunk] = hst[(size_t)i];
+        }
         if (scalar_call && hst[0] != FLINT_SUCCESS) { me->status = hst[0]; return me->status; }   /* :62-76: error return keeps storage */
     }
     if (dealloc) { D.release(); me->dense_allocated = false; }                                     /* :114-118 */
@@ -780,7 +960,33 @@ extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, 
 {
     if (!me) return FLINT_ERROR_PARAMS;
     if (layout != 0 && layout != 1) return me->status = fail(FLINT_ERROR_PARAMS, "layout must be 0 or 1");
-    return interpolate_impl(me, xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, make_exec(exec), false);
+    const ExecCtx ex = make_exec(exec);
+    if (me->shard_N > 0 && !me->shard.empty() && !me->dense.dxint) {
+        /* the last Integrate was sharded over devices: every shard interpolates where its dense output lives and writes the
+         * caller's (host) Yarr at its trajectories' own offsets */
+        if (!ex.host) return me->status = fail(FLINT_ERROR_PARAMS, "the dense output of a sharded Integrate is interpolated into host buffers");
+        if (!me->interp_on) return me->status = FLINT_ERROR_INTP_OFF;
+        const int D = (int)me->shard.size();
+        std::vector<int> rc(D, FLINT_SUCCESS);
+        std::vector<std::string> err(D);
+        std::vector<std::thread> th;
+        for (int k = 0; k < D; ++k)
+            th.emplace_back([&, k]() {
+                Shard sh; sh.Ntot = me->shard_N; sh.D = D; sh.d = k; sh.chunk = me->shard_chunk;
+                ExecCtx e1 = ex;
+                e1.device = me->shard_device[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0;
+                if (shard_count(sh.Ntot, D, k, sh.chunk) == 0) return;
+                rc[k] = interpolate_impl(me->shard[k], xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, e1, false, &sh);
+                if (rc[k] != FLINT_SUCCESS) err[k] = g_last_error;
+            });
+        for (auto& t : th) t.join();
+        int st = FLINT_SUCCESS;
+        for (int k = 0; k < D; ++k) if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
+        const bool dealloc = has_save ? !save_coeffs : true;
+        if (dealloc && st == FLINT_SUCCESS) { me->dense_allocated = false; me->shard_N = 0; }
+        return me->status = st;
+    }
+    return interpolate_impl(me, xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, ex, false);
 }
 
 /* ------------------------------------------------------------------ Info (src/ERKInit.f90:346-394) */

@@ -60,6 +60,17 @@ constexpr int kStiffTestSteps = 1000;            /* STIFFTEST_STEPS, src/ERK.f90
 constexpr double kLastStepExpFac = 1.01;         /* LASTSTEP_EXPFAC, src/ERK.f90:43 */
 constexpr int kMaxSS = FLINT_MAXNUMSTEPSZEVENTS; /* MAXNUMSTEPSZEVENTS, src/ERK.f90:48 */
 
+/* system parameters (flint_sys_create) and, for user functors that declare load_params(const double*, int), the
+ * `params` optional of Integrate (src/FLINT_base.f90:400-468; the reference hands it to F on every call) */
+template <class SYS, class = void> struct has_load_params : std::false_type {};
+template <class SYS>
+struct has_load_params<SYS, std::void_t<decltype(std::declval<SYS&>().load_params((const double*)nullptr, 0))>> : std::true_type {};
+template <class SYS> __device__ __forceinline__ void sys_load(SYS& sys, const KArgs& p)
+{
+    sys.load(p.sp);
+    if constexpr (has_load_params<SYS>::value) sys.load_params(p.params, p.n_params);
+}
+
 /* ---- DetectEvent (:715-741) ---- */
 __device__ __forceinline__ bool detect_event(bool masked_in, int dir, double v0, double v1)
 {
@@ -188,7 +199,7 @@ struct KStore {
     }
 };
 template <class METHOD, class SYS, unsigned SMEM_MASK>
-constexpr int kstore_smem_bytes() { return slot_rank(SMEM_MASK, 32) * comps_stored<SYS>() * step_block<SYS>() * 8; }
+__host__ __device__ constexpr int kstore_smem_bytes() { return slot_rank(SMEM_MASK, 32) * comps_stored<SYS>() * step_block<SYS>() * 8; }
 
 /* ---- context of the rare event path (lives in local memory) ---- */
 template <class METHOD, class SYS>
@@ -537,7 +548,8 @@ __device__ __forceinline__ void state_store(const KArgs& p, long idx, const Lane
     for (int i = 0; i < M; ++i) d[(D::EV0 + i) * c] = L.EV0[i];
     q[SI::TOTAL * c] = L.total; q[SI::ACC * c] = L.acc; q[SI::REJ * c] = L.rej; q[SI::FC * c] = L.fcalls; q[SI::ST * c] = L.st;
     q[SI::FLAGS * c] = (L.LAST ? kFlagLast : 0) | (L.lastRej ? kFlagLastRej : 0) | (L.eventsOn ? kFlagEventsOn : 0) | extra_flags;
-    q[SI::STIFF * c] = (L.stiffMode & 3) | ((L.stiffOut + 1) << 2) | (L.stiffThr << 4) | (L.nonStiffThr << 8);
+    /* only `== 15` (stiffThr) and `== 6` (nonStiffThr) are ever tested (:786-795): counts past them saturate instead of wrapping */
+    q[SI::STIFF * c] = (L.stiffMode & 3) | ((L.stiffOut + 1) << 2) | ((L.stiffThr > 15 ? 15 : L.stiffThr) << 4) | ((L.nonStiffThr > 15 ? 15 : L.nonStiffThr) << 8);
     int evp = (int)(L.evmask & 0xffu) | ((L.evAction & 0xff) << 8);
 #pragma unroll
     for (int i = 0; i < M; ++i) evp |= ((L.EvDir[i] + 1) & 3) << (16 + 2 * i);
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
     const long NN = p.N;
     if (idx >= NN) return;
     SYS sys;
-    sys.load(p.sp);
+    sys_load(sys, p);
     const int m = p.m;
     const bool const_step = p.const_step != 0;
     Lane<SYS> L;
@@ -658,8 +670,16 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
     L.evmask = p.evmask_bits;
     L.eventsOn = p.events_on && L.evmask != 0u;                             /* :175-193 */
     if (early) {
+        /* the reference returns before it touches Xf / Yf / StepSz.  Xf, StepSz and StiffTest keep the caller's values (they are
+         * in/out); every pure output gets a defined value, because on the host-buffer path it is a staging buffer that is
+         * copied back whole: Yf = Y0, counters and counts 0 */
         p.status[idx] = L.st;
         if (p.counters) { p.counters[0 * NN + idx] = 0; p.counters[1 * NN + idx] = 0; p.counters[2 * NN + idx] = 0; p.counters[3 * NN + idx] = 0; }
+#pragma unroll
+        for (int c = 0; c < N; ++c) p.yf[(long)c * NN + idx] = L.Y[c];
+        if (p.ev_count) p.ev_count[idx] = 0;
+        if (p.steps_count) p.steps_count[idx] = 0;
+        if (p.dense_count) p.dense_count[idx] = 0;
         p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
         return;
     }
@@ -708,17 +728,30 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
 }
 
 /* ===================================================================== the hot loop */
-/* EVMODE 0: no events.  1: events located inside the lane loop.  2: steps with events to locate are parked. */
-template <class METHOD, class SYS, bool FMA, int EVMODE>
+/* EVMODE 0: no events.  1: events located inside the lane loop.  2: steps with events to locate are parked.
+ *
+ * GANG (small shards: a few trajectories per lane, e.g. the 2^20-orbit ensemble split over 8 GPUs = 1.73 per lane).  Handing
+ * whole trajectories to lanes then costs max-over-lanes: with 1.73 per lane every warp has a lane that integrates two, the
+ * others idle inside live warps (ncu, 2^17 orbits: 23.7 of 32 lanes per instruction, 20.3 ms against 15.2 at the 2^20 rate,
+ * profiles/r02_notes.md).  The gang-scheduled kernel time-shares the lanes instead: a CTA owns a contiguous n_items / grid of the
+ * pass's items and works in ROUNDS of p.round_len step attempts.  Before a round the CTA selects, among its unfinished
+ * trajectories, the blockDim.x that are furthest BEHIND in the independent variable (progress (X - X0) / (Xf - X0); histogram
+ * threshold in shared memory); every lane loads one, advances it for the round and writes it back.  Trajectories that need more
+ * attempts per unit of x are therefore scheduled more often and all of them reach Xf together: the lanes stay full until the
+ * last rounds, and no lane ever parks or refills on its own (a first version that let lanes swap individually at x milestones
+ * ran 7.9 % of its instructions with < 8 active lanes and pushed the CTA's warps out of step, no_instruction 0.3 -> 2.0).
+ * Arithmetic per trajectory is untouched: results are bit-identical. */
+template <class METHOD, class SYS, bool FMA, int EVMODE, bool GANG = false>
 __global__ void __launch_bounds__(step_block<SYS>(), step_min_blocks<SYS>())
 erk_step_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, M = SYS::M_MAX, PS = METHOD::PSTAR;
     constexpr bool EVENTS = EVMODE != 0;
+    static_assert(!(GANG && EVMODE == 1), "the gang-scheduled kernel has no in-loop event handling");
     /* the plane variant and the general kernel are launched back to back; the flag erk_init_kernel left says which runs */
     if (p.zflag && ((*p.zflag != 0) != is_plane_variant<SYS>())) return;
     SYS sys;
-    sys.load(p.sp);
+    sys_load(sys, p);
     const int m = p.m;
     const bool const_step = p.const_step != 0;
     const double fac = const_step ? 1.0 : kLastStepExpFac;              /* :106-110 */
@@ -744,9 +777,113 @@ erk_step_kernel(const __grid_constant__ KArgs p)
     KStore<METHOD, SYS, METHOD::SMEM_SLOTS> ks;
     ks.s = flint_smem + threadIdx.x;
 
+    /* ---- GANG: this CTA's items, their progress keys and the selection scratch (dynamic shared memory behind the KStore) ---- */
+    constexpr unsigned FULLMASK = 0xffffffffu;
+    __shared__ unsigned s_kmin, s_kmax, s_hist[256];
+    __shared__ int s_nact, s_nsel, s_thr_bin, s_thr_take, s_taken;
+    float* key = reinterpret_cast<float*>(flint_smem + kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>() / 8);   /* [n_local]: progress in [0, 1]; 2 = retired */
+    long lo_item = 0;
+    int n_local = 0, jloc = -1, sweeps = 0;
+    int* sel = nullptr;                                                /* [blockDim.x]: the round's selection */
+    if (GANG) {
+        const long per = (n_items + gridDim.x - 1) / gridDim.x;
+        lo_item = (long)blockIdx.x * per;
+        const long nl = n_items - lo_item;
+        n_local = (int)(nl < 0 ? 0 : (nl > per ? per : nl));
+        sel = reinterpret_cast<int*>(key + ((per + 1) & ~1L));
+        sweeps = (n_local + (int)blockDim.x - 1) / (int)blockDim.x;
+        for (int j = threadIdx.x; j < n_local; j += blockDim.x) {
+            const long i = p.list_in ? (long)p.list_in[lo_item + j] : lo_item + j;
+            float kf = 2.0f;
+            if (i >= 0 && !(p.si[SI::FLAGS * p.scap + i] & kFlagDone)) {
+                const double X0 = p.sd[SD<N, M>::X0 * p.scap + i];
+                kf = (float)((p.sd[SD<N, M>::X * p.scap + i] - X0) / (p.xf[i] - X0));
+                kf = kf >= 0.0f ? (kf <= 1.0f ? kf : 1.0f) : 0.0f;      /* NaN -> 0 */
+            }
+            key[j] = kf;
+        }
+    }
+
     unsigned iter = 0;
+    bool finished = false;
+    while (!finished) {                    /* GANG: one trip = one round; otherwise a single trip */
+    int round_left = 0;
+    if (GANG) {
+        /* ---------------- select the blockDim.x unfinished trajectories with the least progress ---------------- */
+        if (threadIdx.x == 0) { s_kmin = 0x7f800000u; s_kmax = 0u; s_nact = 0; s_nsel = 0; s_taken = 0; }
+        if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
+        __syncthreads();
+        {
+            unsigned kmin = 0x7f800000u, kmax = 0u; int nact = 0;      /* non-negative floats order like their bit patterns */
+            for (int j = threadIdx.x; j < n_local; j += blockDim.x) {
+                const float kf = key[j];
+                if (kf < 1.5f) { const unsigned u = __float_as_uint(kf); kmin = u < kmin ? u : kmin; kmax = u > kmax ? u : kmax; ++nact; }
+            }
+            kmin = __reduce_min_sync(FULLMASK, kmin); kmax = __reduce_max_sync(FULLMASK, kmax); nact = __reduce_add_sync(FULLMASK, nact);
+            if ((threadIdx.x & 31) == 0 && nact) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); atomicAdd(&s_nact, nact); }
+        }
+        __syncthreads();
+        const int nact = s_nact;
+        if (nact == 0) break;
+        const float fmin = __uint_as_float(s_kmin), frange = __uint_as_float(s_kmax) - fmin;
+        const float fscale = frange > 0.0f ? 255.0f / frange : 0.0f;
+        const bool all = nact <= (int)blockDim.x;
+        if (!all) {
+            for (int j = threadIdx.x; j < n_local; j += blockDim.x) {
+                const float kf = key[j];
+                if (kf < 1.5f) atomicAdd(&s_hist[(int)((kf - fmin) * fscale)], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {        /* first bin at which the running count reaches blockDim.x: one warp, 8 bins per lane */
+                unsigned c[8], tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { c[q] = s_hist[threadIdx.x * 8 + q]; tot += c[q]; }
+                unsigned incl = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(FULLMASK, incl, d); if ((int)threadIdx.x >= d) incl += v; }
+                unsigned run = incl - tot;                                /* trajectories in the bins before this lane's */
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (run < blockDim.x && run + c[q] >= blockDim.x) { s_thr_bin = threadIdx.x * 8 + q; s_thr_take = (int)(blockDim.x - run); }
+                    run += c[q];
+                }
+            }
+            __syncthreads();
+        }
+        {
+            const int tb = all ? 256 : s_thr_bin, take = all ? 0 : s_thr_take;
+            for (int w = 0; w < sweeps; ++w) {                         /* warp-aggregated compaction into sel[] */
+                const int j = w * (int)blockDim.x + (int)threadIdx.x;
+                bool pick = false;
+                if (j < n_local) {
+                    const float kf = key[j];
+                    if (kf < 1.5f) {
+                        const int bin = all ? 0 : (int)((kf - fmin) * fscale);
+                        pick = bin < tb || (bin == tb && atomicAdd(&s_taken, 1) < take);
+                    }
+                }
+                const unsigned mk = __ballot_sync(FULLMASK, pick);
+                int base = 0;
+                if ((threadIdx.x & 31) == 0 && mk) base = atomicAdd(&s_nsel, __popc(mk));
+                base = __shfl_sync(FULLMASK, base, 0);
+                if (pick) sel[base + __popc(mk & ((1u << (threadIdx.x & 31)) - 1u))] = j;
+            }
+        }
+        __syncthreads();
+        have = false; jloc = -1;
+        if ((int)threadIdx.x < s_nsel) {
+            jloc = sel[threadIdx.x];
+            const long i = p.list_in ? (long)p.list_in[lo_item + jloc] : lo_item + jloc;
+            state_load<SYS>(p, i, L);
+            idx = i; have = true; powKey = qnan();
+        }
+        round_left = p.round_len;
+    }
     for (;;) {
         /* ---------------- refill: take the next trajectory from the state block ---------------- */
+        if (GANG) {
+            if (round_left-- == 0 || !__any_sync(FULLMASK, have)) break;
+        } else {
         if (!have && !exhausted) {
             const long k = (long)atomicAdd(p.work_counter, 1ULL);     /* every item through the counter (nvcc aggregates it per warp):
                                                                          the kernel does not depend on how many lanes were launched */
@@ -767,9 +904,10 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         /* STEP_BARRIER = K: the CTA meets (and votes on its exit) every K-th iteration; 0: never, each warp votes for itself */
         constexpr int kEvery = has_step_barrier<SYS>::value ? step_barrier_value<SYS>()
                                                             : ((FLINT_SYNC_BLOCK && !(EVMODE == 0 && SYS::INLINE_ACCEL)) ? 1 : 0);
-        if (kEvery == 1) { if (__syncthreads_and(!have && exhausted)) break; }
-        else if (kEvery > 1) { if ((iter++ % (unsigned)(kEvery > 1 ? kEvery : 2)) == 0 && __syncthreads_and(!have && exhausted)) break; }
-        else if (__all_sync(0xffffffffu, !have && exhausted)) break;
+        if (kEvery == 1) { if (__syncthreads_and(!have && exhausted)) { finished = true; break; } }
+        else if (kEvery > 1) { if ((iter++ % (unsigned)(kEvery > 1 ? kEvery : 2)) == 0 && __syncthreads_and(!have && exhausted)) { finished = true; break; } }
+        else if (__all_sync(0xffffffffu, !have && exhausted)) { finished = true; break; }
+        }
 
         /* ---------------- EVMODE 1: finish an accepted step whose events have to be located ---------------- */
         if (EVMODE == 1 && pending) {
@@ -874,6 +1012,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                             p.si[SI::DET * c + idx] = (int)det; p.si[SI::SS * c + idx] = (int)ss;
                             p.list_out[atomicAdd(p.n_out, 1ULL)] = (int)idx;
                             parked = true; have = false;
+                            if (GANG) key[jloc] = 2.0f;
                         }
                     } else {
 #pragma unroll
@@ -908,8 +1047,21 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                 L.LAST = false;
                 if (!const_step && fabs(L.h) * 0.01 <= fabs(L.X) * kEps) L.st = FLINT_ERROR_STEPSZ_TOOSMALL;   /* :632-635 */
             }
-            if (!pending && !parked && !keeps_going<SYS>(p, L)) { store_results<SYS>(p, idx, L); have = false; }
+            if (!pending && !parked && !keeps_going<SYS>(p, L)) {
+                store_results<SYS>(p, idx, L); have = false;
+                if (GANG) key[jloc] = 2.0f;
+            }
         }
+    }
+    if (GANG) {                            /* end of the round: back to the state block, with the new progress as the key */
+        if (have) {
+            state_store<SYS>(p, idx, L, 0);
+            const double X0 = p.sd[SD<N, M>::X0 * p.scap + idx];
+            float kf = (float)((L.X - X0) / (L.Xf - X0));
+            key[jloc] = kf >= 0.0f ? (kf <= 1.0f ? kf : 1.0f) : 0.0f;
+        }
+        __syncthreads();                   /* state blocks and keys are read by other lanes of this CTA in the next round */
+    }
     }
 }
 
@@ -928,7 +1080,7 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
     if (j >= n_parked) return;
     const long idx = p.list_in[j];
     SYS sys;
-    sys.load(p.sp);
+    sys_load(sys, p);
     Lane<SYS> L;
     const int flags = state_load<SYS>(p, idx, L);
     const long c = p.scap;
@@ -977,7 +1129,7 @@ __global__ void __launch_bounds__(128, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense
     int nacc = p.dense_count[t];
     if (nacc > p.dense_cap) nacc = (int)p.dense_cap;
     SYS sys;
-    sys.load(p.sp);
+    sys_load(sys, p);
     for (int s = blockIdx.y; s < nacc; s += gridDim.y) {
         /* with two warps per sub-partition every DRAM round trip is exposed (ncu: a quarter of all stall samples sat on the
          * flag test and on the first use of the log): flag and log are requested together, and the next step's lines are
@@ -1014,19 +1166,20 @@ cudaError_t launch_step(const KArgs& a, int sm_count, long n_items, int block_re
     constexpr int BLOCK = step_block<SYS>();
     int block = (block_req > 0 && block_req < BLOCK) ? (block_req + 31) / 32 * 32 : BLOCK;
     if (smem > 0) block = BLOCK;                            /* the shared-memory layout is compiled for this block size */
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
+    if (smem > 48 * 1024) {                                 /* per device context, and cheap: not cached */
         const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
-    static thread_local int cached_block = -1, cached_bps = 0;   /* one occupancy query per CTA size and host thread */
-    if (cached_block != block) {
+    /* one occupancy query per (device, CTA size) and host thread: handles on different devices may launch from different threads */
+    static thread_local int cached_block = -1, cached_bps = 0, cached_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cached_block != block || cached_dev != dev) {
         int q = 0;
         const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block, smem);
         if (e != cudaSuccess) return e;
         cached_bps = q < 1 ? 1 : q;
-        cached_block = block;
+        cached_block = block; cached_dev = dev;
     }
     int bps = cached_bps;
     if (bps_req > 0 && bps_req < bps) bps = bps_req;
@@ -1034,6 +1187,28 @@ cudaError_t launch_step(const KArgs& a, int sm_count, long n_items, int block_re
     const long need = (n_items + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if constexpr (EVMODE != 1) {
+        /* small shards: more than one but fewer than ~8 trajectories per lane -> the gang-scheduled kernel (see erk_step_kernel) */
+        const long lanes = grid * block;
+        int S = 0;
+        if (a.round_req >= 2) S = a.round_req;
+        else if (a.round_req == 0 && a.n_items_exact && n_items > lanes && n_items < 8 * lanes) S = n_items < 4 * lanes ? 64 : 128;
+        if (S > 4096) S = 4096;
+        if (S >= 2 && a.n_items_exact) {
+            const long per = (n_items + grid - 1) / grid;
+            const long smem2 = smem + ((per + 1) & ~1L) * 4 + (long)block * 4;
+            if (smem2 <= 200 * 1024) {
+                KArgs b = a;
+                b.round_len = S;
+                if (smem2 > 48 * 1024) {
+                    const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                    if (e != cudaSuccess) return e;
+                }
+                erk_step_kernel<METHOD, SYS, FMA, EVMODE, true><<<(unsigned)grid, block, (size_t)smem2, s>>>(b);
+                return cudaGetLastError();
+            }
+        }
+    }
     erk_step_kernel<METHOD, SYS, FMA, EVMODE><<<(unsigned)grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
@@ -1053,7 +1228,10 @@ cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
 template <class METHOD, class SYS, bool FMA>
 cudaError_t launch_dense(const KArgs& a, int grid, int block, cudaStream_t s)
 {
-    long gy = 4L * 148 * 16 * 32 / (a.N > 0 ? a.N : 1);              /* ~4 waves of threads over the device */
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long gy = 4L * (sms > 0 ? sms : 148) * 16 * 32 / (a.N > 0 ? a.N : 1);   /* ~4 waves of threads over the device */
     if (gy < 1) gy = 1;
     if (gy > a.dense_cap) gy = a.dense_cap;
     if (gy > 4096) gy = 4096;

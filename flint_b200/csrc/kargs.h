@@ -84,6 +84,10 @@ struct KArgs {
     int* list_out; unsigned long long* n_out;    /* EVMODE 2: trajectories parked by this pass */
     int* zflag;                                  /* NULL, or: 1 = every trajectory lies in the system's invariant plane (plane-variant kernel runs) */
     unsigned long long* work_counter;
+    /* small shards (erk_kernel.cuh: GANG): round_req 0 = automatic, 1 = never, k >= 2 = gang-scheduled rounds of k step attempts;
+     * n_items_exact: the host knows the pass's item count (synchronous calls); round_len is filled by launch_step */
+    int round_req, n_items_exact, round_len;
+    double params[8]; int n_params;              /* Integrate(params=...) forwarded to user functors (systems.cuh: load_params) */
     double coef[FLINT_NCOEF];    /* the method's Butcher / error / dense coefficients (filled by the host, capi.cu) */
     double powc[32];             /* constants of the controller's pow (arith.cuh: det_pow_constants) */
 };
@@ -103,7 +107,6 @@ struct InterpArgs {
 cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
 cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
                                 unsigned long long c3, cudaStream_t);   /* registry.cu */
-cudaError_t launch_any_differs(const int* a, const int* b, long n, unsigned long long* flag, cudaStream_t);
 
 /* registry of compiled integrate kernels (filled by static initialisers in inst_*.cu) */
 typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t);

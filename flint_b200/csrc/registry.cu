@@ -38,18 +38,6 @@ cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, 
     return cudaGetLastError();
 }
 
-/* flag[0] = 1 if a[i] != b[i] anywhere (event counts at the end of a call against their snapshot, capi.cu) */
-__global__ void any_differs_kernel(const int* __restrict__ a, const int* __restrict__ b, long n, unsigned long long* flag)
-{
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && a[i] != b[i]) *flag = 1ULL;
-}
-cudaError_t launch_any_differs(const int* a, const int* b, long n, unsigned long long* flag, cudaStream_t s)
-{
-    any_differs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, n, flag);
-    return cudaGetLastError();
-}
-
 }  // namespace flint
 
 extern "C" int flint_b200_kernel_count(void) { return flint::kernel_count(); }

@@ -58,9 +58,11 @@ def uniform01(index, comp=0, seed=SEED):
     return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
-def cr3bp_ensemble(N, start=0, spread=1e-6):
-    """Config 3/4 ICs: y0_i = (0.994*(1 + spread*u_i), 0, 0, 0, -2.0015..., 0), SoA (6, N)."""
-    i = np.arange(start, start + N, dtype=np.uint64)
+def cr3bp_ensemble(N, start=0, spread=1e-6, index=None):
+    """Config 3/4 ICs: y0_i = (0.994*(1 + spread*u_i), 0, 0, 0, -2.0015..., 0), SoA (6, N).  index: the trajectory indices
+    (any order, e.g. a shard of the ensemble, api.shard_indices) instead of start .. start+N-1."""
+    i = np.arange(start, start + N, dtype=np.uint64) if index is None else np.asarray(index, dtype=np.uint64)
+    N = len(i)
     y0 = np.repeat(ARENSTORF_Y0[:, None], N, axis=1)
     y0[0] = ARENSTORF_Y0[0] * (1.0 + spread * uniform01(i, 0))
     return np.ascontiguousarray(y0)

@@ -76,6 +76,8 @@ enum {
 
 #define FLINT_MAX_N 8
 #define FLINT_MAX_M 4
+#define FLINT_MAX_DEVICES 16
+#define FLINT_SHARD_CHUNK 4096         /* trajectories per chunk of the block-cyclic deal over devices / ranks */
 #define FLINT_MAXNUMSTEPSZEVENTS 4     /* src/ERK.f90:48 */
 
 typedef struct flint_sys flint_sys_t; /* DiffEqSys: n, m, functor ids, system parameters */
@@ -104,7 +106,8 @@ typedef struct {
     int arith;                                    /* FLINT_ARITH_* (extension)                                  */
 } flint_init_opts;
 
-/* `present` bits for the optionals of Integrate (src/FLINT_base.f90:400-468) */
+/* `present` bits for the optionals of Integrate (src/FLINT_base.f90:400-468).  Xint/Yint, EventStates and StiffTest are
+ * present when their pointer arguments are non-NULL: the three bits named after them are accepted and not consulted. */
 enum {
     FLINT_INT_CONST_STEPSZ = 1 << 0, FLINT_INT_STEP_ADVANCE = 1 << 1, FLINT_INT_INTSTEPS_ON = 1 << 2,
     FLINT_INT_XINT_YINT = 1 << 3, FLINT_INT_EVENT_MASK = 1 << 4, FLINT_INT_EVENT_STATES = 1 << 5,
@@ -116,7 +119,9 @@ typedef struct {
     int step_advance;              /* StepAdvance    */
     int int_steps_on;              /* IntStepsOn     */
     int event_mask[FLINT_MAX_M];   /* EventMask(m)   */
-    int n_params; const double* params;   /* params(:) forwarded to F */
+    int n_params; const double* params;   /* params(:): at most 8 values, forwarded to user functors that declare load_params()
+                                             (csrc/systems.cuh); the built-in systems ignore them, as the reference's own F do.
+                                             More than 8 values: FLINT_ERROR_PARAMS */
 } flint_int_opts;
 
 /* Natural-step output (Xint/Yint, `allocatable, intent(out)` in the reference: caller-allocated
@@ -151,7 +156,24 @@ typedef struct {
     int pipeline;       /* FLINT_MEM_HOST: k >= 2 = the call runs as k chunks of trajectories on two streams, so that the
                            host<->device copies of one chunk travel while another computes (pays for short integrations,
                            where the copies are a large part of the call); 0 / 1 = one chunk.  Results are identical. */
+    int round_len;      /* small shards (a few trajectories per GPU lane): the step kernel time-shares its lanes in rounds of k step
+                           attempts, each round on the trajectories furthest behind in x, so that all lanes stay busy until the
+                           ensemble finishes together.  0 = automatic (between 1 and 8 trajectories per lane),
+                           1 = never, k >= 2 = rounds of k attempts.  Results are identical. */
+    int n_devices;      /* FLINT_MEM_HOST: > 1 = the ensemble is sharded over devices[0 .. n_devices-1]: chunks of shard_chunk
+                           trajectories are dealt round-robin (block-cyclic), each device runs its shard on its own
+                           stream from its own host thread, results land at the caller's offsets.  No collective exists on this
+                           path.  0 / 1 = the single `device`.  Results are identical to the one-device call. */
+    int devices[FLINT_MAX_DEVICES];
+    long shard_chunk;   /* trajectories per dealt chunk; 0 = FLINT_SHARD_CHUNK */
 } flint_exec;
+
+/* ---- the partition of an ensemble over shards (devices of one call, or ranks of a multi-process job): trajectory index space
+ * [0, N) in chunks of `chunk`, chunk c -> shard c mod n_shards.  Pure host arithmetic (no CUDA call). ---- */
+long flint_b200_shard_count(long N, int n_shards, int shard, long chunk);                 /* trajectories of `shard` */
+long flint_b200_shard_global_index(long N, int n_shards, int shard, long chunk, long local_index);   /* -1 when out of range */
+/* out[0 .. count-1] = global indices of the shard's trajectories in local order; returns count */
+long flint_b200_shard_indices(long N, int n_shards, int shard, long chunk, long* out);
 
 /* ---- DiffEqSys ---- */
 flint_sys_t* flint_sys_create(int system_id, int eventset_id, int n, int m, const double* sysparams, int nsysparams);

@@ -15,7 +15,6 @@ working precision real64:
     the theta^6 column is silently dropped (src/ButcherTableaus.f90:975,1095-1152).
 
 Output: C arrays with hex-float literals (bit-exact), 0-based, written to
-  flint_b200/csrc/flint_tableaus.h   (product, usable from __host__ __device__ code)
   oracle/oracle_tableaus.h           (oracle; same numbers, separate file so the
                                       product never includes anything under oracle/)
 
@@ -255,8 +254,8 @@ def main():
     ap.add_argument("--root", default=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     args = ap.parse_args()
     body, report = build(args.ref)
-    for rel, guard in (("flint_b200/csrc/flint_tableaus.h", "FLINT_B200_TABLEAUS_H"),
-                       ("oracle/oracle_tableaus.h", "FLINT_ORACLE_TABLEAUS_H")):
+    # the product's coefficients are generated into erk_methods_gen.cuh by tools/gen_kernels.py (which imports this parser)
+    for rel, guard in (("oracle/oracle_tableaus.h", "FLINT_ORACLE_TABLEAUS_H"),):
         path = os.path.join(args.root, rel)
         os.makedirs(os.path.dirname(path), exist_ok=True)
         with open(path, "w") as f:
