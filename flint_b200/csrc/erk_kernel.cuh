@@ -49,6 +49,9 @@
 #define FLINT_B200_ERK_KERNEL_CUH
 
 #include <type_traits>
+#ifdef FLINT_GANG_TRACE
+#include <cstdio>
+#endif
 #include "erk_methods_gen.cuh"
 #include "systems.cuh"
 
@@ -870,6 +873,9 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             }
         }
         __syncthreads();
+#ifdef FLINT_GANG_TRACE
+        if (threadIdx.x == 0 && blockIdx.x == 0) printf("round nact %d nsel %d fmin %.4f fmax %.4f clk %lld\n", nact, s_nsel, fmin, fmin + frange, clock64());
+#endif
         have = false; jloc = -1;
         if ((int)threadIdx.x < s_nsel) {
             jloc = sel[threadIdx.x];
@@ -877,7 +883,8 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             state_load<SYS>(p, i, L);
             idx = i; have = true; powKey = qnan();
         }
-        round_left = p.round_len;
+        /* near the end a round outlasts most of its trajectories (lanes idle until the CTA meets again): shorter rounds there */
+        round_left = fmin > 0.96f ? (p.round_len >> 2) + 1 : (fmin > 0.88f ? (p.round_len >> 1) + 1 : p.round_len);
     }
     for (;;) {
         /* ---------------- refill: take the next trajectory from the state block ---------------- */
