@@ -56,18 +56,44 @@ struct Workspace {                     /* trajectory state block + work lists of
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; device = -1; }
 };
 
-struct DenseStore {                    /* device-resident Xint / Bip of the last Integrate with InterpOn */
+/* Device-resident dense output of the last Integrate with InterpOn (kargs.h: DenseView): capacity levels of step records.
+ * kind_coef: the records are (to be) coefficient records, rstride holds them; else step logs only (the fused Interpolate). */
+struct DenseStore {
     int device = -1;
-    long N = 0, cap = 0;
-    int nI = 0, pstar = 0, rstride = 0;
-    double* dxint = nullptr; double* dbip = nullptr; int* dcount = nullptr; unsigned char* dflag = nullptr;
+    long N = 0;
+    int n = 0, nI = 0, pstar = 0, rstride = 0;
+    bool kind_coef = false, events = false;
+    int nlev = 0;
+    long cap[FLINT_DENSE_LEVELS] = {0}, rows[FLINT_DENSE_LEVELS] = {0};
+    double* base[FLINT_DENSE_LEVELS] = {nullptr};
+    int* slot[FLINT_DENSE_LEVELS] = {nullptr};
+    int* dcount = nullptr;
+    int* dzflag = nullptr;             /* device word: 1 = every trajectory lies in the system's invariant plane (plane-variant kernels) */
     void release()
     {
-        if (dxint) cudaFree(dxint);
-        if (dbip) cudaFree(dbip);
+        if (dzflag) cudaFree(dzflag);
+        dzflag = nullptr;
+        for (int l = 0; l < FLINT_DENSE_LEVELS; ++l) {
+            if (base[l]) cudaFree(base[l]);
+            if (slot[l]) cudaFree(slot[l]);
+            base[l] = nullptr; slot[l] = nullptr; cap[l] = rows[l] = 0;
+        }
         if (dcount) cudaFree(dcount);
-        if (dflag) cudaFree(dflag);
-        dxint = dbip = nullptr; dcount = nullptr; dflag = nullptr; N = cap = 0;
+        dcount = nullptr; N = 0; nlev = 0;
+    }
+    bool allocated() const { return nlev > 0 && base[0] != nullptr; }
+    flint::DenseView view() const
+    {
+        flint::DenseView v{};
+        v.nlev = nlev; v.rstride = rstride; v.cum[0] = 0;
+        for (int l = 0; l < nlev; ++l) { v.cum[l + 1] = v.cum[l] + cap[l]; v.base[l] = base[l]; v.slot[l] = slot[l]; }
+        return v;
+    }
+    size_t bytes() const
+    {
+        size_t b = 0;
+        for (int l = 0; l < nlev; ++l) b += (size_t)rows[l] * (size_t)cap[l] * (size_t)rstride * 8;
+        return b;
     }
 };
 
@@ -101,6 +127,7 @@ struct flint_erk {
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};
     int pipe_device = -1;
     bool dense_is_scalar = false;
+    bool dense_plane_ok = false;       /* the plane-variant kernels were eligible for the call that filled the dense store */
     bool dense_allocated = false;      /* allocated(me%Xint) */
     double last_kernel_ms = 0.0;       /* device time of the last batch Integrate of this handle (CUDA events on its stream) */
     unsigned long long* pinned = nullptr;   /* page-locked words the kernels' counters are read back into */
@@ -330,7 +357,7 @@ struct DevBuf {
 
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
-    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0, round_len = 0;
+    long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0, round_len = 0, dense_mode = 0;
     int n_devices = 0; int devices[FLINT_MAX_DEVICES] = {0}; long shard_chunk = 0;
 };
 
@@ -386,12 +413,42 @@ static bool shard_copy(const Shard& sh, long N, long off, long cnt, void* dst, c
     return ok;
 }
 
+/* what Init parsed, as the kernels' parameter block (everything that does not depend on one Integrate call) */
+static void fill_static_kargs(const flint_erk* me, KArgs& a)
+{
+    const flint_sys& sys = *me->sys;
+    a.n = sys.n; a.m = sys.m; a.evset = sys.eventset_id;
+    for (int i = 0; i < 8; ++i) a.sp[i] = sys.sp[i];
+    /* derived parameter, computed once here with the same IEEE operation the reference's F performs on every call
+     * (`1.0_WP - mu`, tests/test_CR3BP.f90:178): the kernels read it from the parameter block */
+    if (sys.system_id == FLINT_SYS_CR3BP_PLANAR || sys.system_id == FLINT_SYS_CR3BP_SPATIAL) a.sp[7] = 1.0 - a.sp[0];
+    a.max_steps = me->max_steps;
+    for (int i = 0; i < FLINT_MAX_N; ++i) { a.tol.a[i] = me->atol[i]; a.tol.r[i] = me->rtol[i]; }
+    a.tol.scalar = me->scalar_tol ? 1 : 0;
+    a.hmax_opt = me->max_step;
+    for (int i = 0; i < 6; ++i) a.szp[i] = me->szp[i];
+    for (int i = 0; i < FLINT_MAX_M; ++i) { a.ev_stepsz[i] = me->ev_stepsz[i]; a.ev_opt[i] = me->ev_opt[i]; a.etol[i] = me->etol[i]; }
+    a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
+}
+
+/* record size of the dense store: step logs (2n+2 doubles; 3n+3 with events: the event code's steps carry h_stage and Y1), or
+ * room for the coefficient record the log is turned into, + the kind, rounded to an even count (16-byte alignment) */
+static int dense_rstride(const flint_erk* me, bool coef)
+{
+    const int n = me->sys->n;
+    int r = me->events_on ? 3 * n + 3 : 2 * n + 2;
+    if (coef && me->nI * (me->pstar + 1) + 2 > r) r = me->nI * (me->pstar + 1) + 2;
+    r += 1;
+    return r + (r & 1);
+}
+
 static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double* x0, const double* y0, double* xf,
                           double* yf, double* stepsz, const flint_int_opts* io, int* counters, int* status,
                           flint_steps_out* steps, flint_events_out* events, int* stifftest, const ExecCtx& ex,
                           bool scalar_call, const Shard* shard_in = nullptr)
 {
     if (!me->inited || !me->sys) return me->status = FLINT_ERROR_INIT_REQD;
+    g_last_error.clear();
     const flint_sys& sys = *me->sys;
     const int n = sys.n, m = sys.m;
     static const flint_int_opts kNoOpts{};
@@ -435,25 +492,15 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     }
 
     KArgs a{};
-    a.N = N; a.n = n; a.m = m; a.evset = sys.eventset_id;
-    for (int i = 0; i < 8; ++i) a.sp[i] = sys.sp[i];
-    /* derived parameter, computed once here with the same IEEE operation the reference's F performs on every call
-     * (`1.0_WP - mu`, tests/test_CR3BP.f90:178): the kernels read it from the parameter block */
-    if (sys.system_id == FLINT_SYS_CR3BP_PLANAR || sys.system_id == FLINT_SYS_CR3BP_SPATIAL) a.sp[7] = 1.0 - a.sp[0];
-    a.max_steps = me->max_steps;
-    for (int i = 0; i < FLINT_MAX_N; ++i) { a.tol.a[i] = me->atol[i]; a.tol.r[i] = me->rtol[i]; }
-    a.tol.scalar = me->scalar_tol ? 1 : 0;
-    a.hmax_opt = me->max_step;
-    for (int i = 0; i < 6; ++i) a.szp[i] = me->szp[i];
+    fill_static_kargs(me, a);
+    a.N = N;
     a.const_step = const_step; a.step_once = step_once;
     a.stiff_present = stiff_present; a.stiff_mode = 0;
     a.events_on = events_on; a.evmask_bits = evmask;
-    for (int i = 0; i < FLINT_MAX_M; ++i) { a.ev_stepsz[i] = me->ev_stepsz[i]; a.ev_opt[i] = me->ev_opt[i]; a.etol[i] = me->etol[i]; }
     a.x0_scalar = x0_scalar;
     a.steps_on = int_steps;
     a.steps_cap = int_steps ? steps->cap : 0;
     a.ev_cap = events_on ? events->cap : 0;
-    a.nI = me->nI; for (int i = 0; i < FLINT_MAX_N; ++i) a.istates[i] = me->istates[i];
     a.round_req = ex.round_len;
     if (io->present & FLINT_INT_PARAMS) { a.n_params = io->n_params; for (int i = 0; i < io->n_params; ++i) a.params[i] = io->params[i]; }
 
@@ -555,32 +602,49 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             if (int_steps) { c.xint = steps->xint; c.yint = steps->yint; c.steps_count = steps->count; }
             if (!status) return fail(FLINT_ERROR_PARAMS, "status[] is required");
         }
-        /* ---- dense storage owned by the object (src/ERKInit.f90:321-332: sized for MaxSteps) ---- */
+        /* ---- dense storage owned by the object.  The reference sizes it for MaxSteps + 1 (src/ERKInit.f90:321-332); here level 0
+         * holds cap0 steps per trajectory and the store grows by levels for the trajectories that need more (below): nothing is
+         * ever dropped.  cap0: flint_exec.dense_cap, else what a third of the free device memory holds, at most MaxSteps. ---- */
         if (dense) {
-            long cap = ex.dense_cap > 0 ? ex.dense_cap : me->max_steps;
-            if (cap > me->max_steps) cap = me->max_steps;
             DenseStore& D = me->dense;
-            /* a step slot holds the step's coefficients, (pstar+1)*nI doubles, and before that its log, 2n+2 doubles */
-            int rstride = me->nI * (me->pstar + 1);
-            if (rstride < 2 * n + 2) rstride = 2 * n + 2;
-            rstride += rstride & 1;
-            if (D.device != ex.device || D.N != cnt || D.cap != cap || D.nI != me->nI || D.pstar != me->pstar || D.rstride != rstride || !D.dxint) {
-                D.release();
-                const size_t nb = szN * (size_t)cap * (size_t)rstride;
-                if (cudaMalloc(&D.dxint, szN * (size_t)(cap + 1) * 8) != cudaSuccess || cudaMalloc(&D.dbip, nb * 8) != cudaSuccess ||
-                    cudaMalloc(&D.dcount, szN * 4) != cudaSuccess || cudaMalloc(&D.dflag, szN * (size_t)cap) != cudaSuccess) {
-                    cudaGetLastError(); D.release();
-                    return fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; set flint_exec.dense_cap");
-                }
-                D.device = ex.device; D.N = cnt; D.cap = cap; D.nI = me->nI; D.pstar = me->pstar; D.rstride = rstride;
+            const bool coef = ex.dense_mode == 1;
+            const int rstride = dense_rstride(me, coef);
+            long cap = ex.dense_cap > 0 ? ex.dense_cap : 0;
+            if (cap <= 0) {
+                size_t fr = 0, tot = 0;
+                cudaMemGetInfo(&fr, &tot);
+                fr += D.bytes();                                       /* the previous call's store is reused or released */
+                cap = (long)(fr / 3 / (szN * (size_t)rstride * 8));
+                if (cap > 4096) cap = 4096;
             }
-            c.dense_cap = cap; c.dxint = D.dxint; c.dbip = D.dbip; c.dense_count = D.dcount; c.dense_rstride = rstride; c.dflag = D.dflag;
+            if (cap > me->max_steps) cap = me->max_steps;
+            cap = (cap + 127) / 128 * 128;                             /* a CTA of the dense kernels never straddles two levels */
+            if (cap < 128) cap = 128;
+            if (D.device != ex.device || D.N != cnt || D.cap[0] != cap || D.nI != me->nI || D.pstar != me->pstar || D.rstride != rstride ||
+                D.kind_coef != coef || !D.allocated()) {
+                D.release();
+                if (cudaMalloc(&D.base[0], szN * (size_t)cap * (size_t)rstride * 8) != cudaSuccess || cudaMalloc(&D.dcount, szN * 4) != cudaSuccess ||
+                    cudaMalloc(&D.dzflag, 8) != cudaSuccess) {
+                    cudaGetLastError(); D.release();
+                    return fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory; lower flint_exec.dense_cap");
+                }
+                D.device = ex.device; D.N = cnt; D.n = n; D.nI = me->nI; D.pstar = me->pstar; D.rstride = rstride; D.kind_coef = coef;
+                D.cap[0] = cap; D.rows[0] = cnt;
+            }
+            for (int l = 1; l < FLINT_DENSE_LEVELS; ++l) {            /* levels a previous call added */
+                if (D.base[l]) cudaFree(D.base[l]);
+                if (D.slot[l]) cudaFree(D.slot[l]);
+                D.base[l] = nullptr; D.slot[l] = nullptr; D.cap[l] = D.rows[l] = 0;
+            }
+            D.nlev = 1; D.events = me->events_on;
+            c.dv = D.view(); c.dense_count = D.dcount;
             me->dense_is_scalar = scalar_call;
         }
         /* ---- trajectory state block, work lists and counters (erk_kernel.cuh) ---- */
-        const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = szN * 4;
+        const size_t sd_b = szN * (size_t)ke->n_state_doubles * 8, si_b = szN * (size_t)ke->n_state_ints * 4, li_b = (szN + (szN & 1)) * 4;
+        const int n_lists = dense ? 4 : 2;                     /* parked lists A, B; suspended-for-capacity lists C, D (InterpOn) */
         {
-            const size_t need_b = sd_b + si_b + 2 * li_b + 64;
+            const size_t need_b = sd_b + si_b + (size_t)n_lists * li_b + 72;
             Workspace& W = me->ws[slot];
             if (W.device != ex.device || W.bytes < need_b) {
                 W.release();
@@ -591,43 +655,54 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             c.sd = (double*)base; c.si = (int*)(base + sd_b); c.scap = cnt;
         }
         int* listA = (int*)((char*)me->ws[slot].ptr + sd_b + si_b);
-        int* listB = listA + szN;
-        unsigned long long* ctr = (unsigned long long*)(listB + szN + ((szN & 1) ? 1 : 0));   /* 8-byte aligned: [0] work, [1] |A|, [2] |B| */
+        int* listB = listA + li_b / 4;
+        int* listCD[2] = {listB + li_b / 4, listB + 2 * (li_b / 4)};
+        unsigned long long* ctr = (unsigned long long*)((char*)me->ws[slot].ptr + (sd_b + si_b + (size_t)n_lists * li_b + 7) / 8 * 8);
 
         /* [0] work counter (every item is handed out through it), [1] |A|, [2] |B|, [3] low word: the plane flag, cleared by
-         * erk_init_kernel.  Set on the device: a pageable H2D copy would make the host wait for everything queued on this stream */
-        if (!cuda_ok(flint::launch_set_counters(ctr, 0ULL, 0ULL, 0ULL, 1ULL, s), "work counters")) return FLINT_ERROR;
+         * erk_init_kernel, [4] |C|, [5] |D|.  Set on the device: a pageable H2D copy would make the host wait for everything
+         * queued on this stream */
+        if (!cuda_ok(flint::launch_set_counters(ctr, 0ULL, 0ULL, 0ULL, 1ULL, s), "work counters") ||
+            !cuda_ok(cudaMemsetAsync(ctr + 4, 0, 16, s), "work counters")) return FLINT_ERROR;
         g_launches += 1;
         c.work_counter = ctr;
-        c.n_items_exact = 1;                                   /* pass 0 runs all cnt trajectories (gang-scheduled kernel, erk_kernel.cuh) */
         c.zflag = try_plane ? (int*)(ctr + 3) : nullptr;
         const int grid_all = (int)((cnt + 127) / 128);
+        /* InterpOn: a trajectory whose levels of the dense store are full is suspended on list C / D; synchronous calls add a
+         * level and resume it (below).  Calls that never read a count back cannot: they keep what fits (Interpolate then
+         * reports FLINT_ERROR_INTP_ARRAY for those trajectories, the reference's answer to a full Xint) */
+        const bool can_grow = dense && !fixed_schedule;
+        int ovf = 0;                                           /* index of the list being filled */
+        if (dense) { c.dense_avail = can_grow ? c.dv.capacity() : (1L << 62); c.ovf_list = listCD[ovf]; c.n_ovf = ctr + 4 + ovf; }
 
-        if (e0) cudaEventRecord(e0, s);
-        cudaError_t le = ke->init(c, grid_all, 128, s);
-        g_launches += 1;
-        if (le == cudaSuccess && !park) {
-            c.list_in = nullptr; c.n_in = nullptr; c.list_out = nullptr; c.n_out = nullptr;
-            if (try_plane) { le = ke->step_plane(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* returns at once unless the flag is set */
-            if (le == cudaSuccess) { le = ke->step(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
-        } else if (le == cudaSuccess) {
-            /* pass 0 over [0, N); then rounds of {locate the parked events, resume}.  Synchronous calls read the
-             * parked count and stop when it is zero; the fixed schedule runs a set number of rounds (empty kernels return
-             * at once).  The last round resumes with in-loop event handling, so it always finishes. */
+        /* one sweep over a set of trajectories -- all cnt of them (in == nullptr) or a list -- to their end, to a parked event
+         * (located in rounds of {event kernel, resume}) or to a full dense store */
+        auto sweep = [&](const int* in, const unsigned long long* n_in, long n_items) -> cudaError_t {
+            cudaError_t le = cudaSuccess;
+            c.n_items_exact = 1;                               /* the host knows how many trajectories this pass runs (gang-scheduled kernel) */
+            if (!park) {
+                c.list_in = in; c.n_in = n_in; c.list_out = nullptr; c.n_out = nullptr;
+                if (try_plane) { le = ke->step_plane(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* returns at once unless the flag is set */
+                if (le == cudaSuccess) { le = ke->step(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                return le;
+            }
+            /* pass 0; then rounds of {locate the parked events, resume}.  Synchronous calls read the parked count and stop when
+             * it is zero; the fixed schedule runs a set number of rounds (empty kernels return at once).  The last round
+             * resumes with in-loop event handling, so it always finishes. */
             const int max_rounds = fixed_schedule ? 3 : 64;
             int cur = 1;                                               /* index of the counter of the list being filled */
-            c.list_in = nullptr; c.n_in = nullptr; c.list_out = listA; c.n_out = ctr + 1;
-            if (try_plane) { le = ke->step_plane(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
-            if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, cnt, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+            c.list_in = in; c.n_in = n_in; c.list_out = listA; c.n_out = ctr + 1;
+            if (try_plane) { le = ke->step_plane(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
             for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
-                long n_parked = cnt;
+                long n_parked = n_items;
                 if (!fixed_schedule) {
                     /* the parked count through a page-locked word: a pageable destination would be staged by the driver */
                     if (!cuda_ok(cudaMemcpyAsync(me->pinned, ctr + cur, 8, cudaMemcpyDeviceToHost, s), "D2H parked count") ||
-                        !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
+                        !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) return cudaErrorUnknown;
                     n_parked = (long)me->pinned[0];
                     if (n_parked == 0) break;
-                    if (round >= 1) reparked = true;           /* events located after the early copy of the records */
+                    if (round >= 1 || early_done) reparked = true;     /* events located after the early copy of the records */
                 }
                 int* lcur = cur == 1 ? listA : listB;
                 int* loth = cur == 1 ? listB : listA;
@@ -638,15 +713,15 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 g_launches += 1;
                 if (le != cudaSuccess) break;
                 bool issue_early = false;
-                if (early_ev && round == 0) {                  /* stream order: the marker sits between the event kernel and the resume pass */
+                if (early_ev && round == 0 && !early_done) {   /* stream order: the marker sits between the event kernel and the resume pass */
                     const bool ok = cuda_ok(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming), "cudaEventCreate") &&
                                     cuda_ok(cudaEventRecord(ev_ready, s), "cudaEventRecord");
-                    if (!ok) { le = cudaErrorUnknown; break; }
+                    if (!ok) return cudaErrorUnknown;
                     issue_early = true;
                 }
                 /* the event kernel re-armed the work counter; a pass never launches more lanes than it has items */
                 const bool last = round == max_rounds - 1;
-                if (last) { c.zflag = nullptr; le = ke->step(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* in-loop events, general kernel */
+                if (last) { int* zf = c.zflag; c.zflag = nullptr; le = ke->step(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; c.zflag = zf; }   /* in-loop events, general kernel */
                 else {
                     if (try_plane) { le = ke->step_plane(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
                     if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
@@ -655,19 +730,68 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                     cudaStream_t s2 = me->pipe_stream[1];
                     const bool ok = cuda_ok(cudaStreamWaitEvent(s2, ev_ready, 0), "cudaStreamWaitEvent") &&
                                     copy2d(events->rec, c.ev_rec, 8, (size_t)(n + 2) * (size_t)c.ev_cap, false, "early D2H ev_rec", s2);
-                    if (!ok) { le = cudaErrorUnknown; break; }
+                    if (!ok) return cudaErrorUnknown;
                     early_done = true;
                 }
                 cur = oth;
             }
+            return le;
+        };
+
+        if (e0) cudaEventRecord(e0, s);
+        cudaError_t le = ke->init(c, grid_all, 128, s);
+        g_launches += 1;
+        if (le == cudaSuccess) le = sweep(nullptr, nullptr, cnt);
+        /* ---- InterpOn: trajectories suspended with a full dense store get a new level, 4x as deep, and are resumed ---- */
+        while (le == cudaSuccess && can_grow) {
+            if (!cuda_ok(cudaMemcpyAsync(me->pinned, ctr + 4 + ovf, 8, cudaMemcpyDeviceToHost, s), "D2H suspended count") ||
+                !cuda_ok(cudaStreamSynchronize(s), "kernel execution")) { le = cudaErrorUnknown; break; }
+            const long n_susp = (long)me->pinned[0];
+            if (n_susp == 0) break;
+            DenseStore& D = me->dense;
+            if (D.nlev >= FLINT_DENSE_LEVELS) { g_last_error = "dense-output storage: level limit reached"; le = cudaErrorUnknown; break; }
+            const int l = D.nlev;
+            long capl = 4 * D.cap[l - 1];
+            const long held = c.dv.capacity();
+            if (held + capl > me->max_steps + 127) capl = (me->max_steps - held + 127) / 128 * 128;
+            if (capl < 128) capl = 128;
+            if (cudaMalloc(&D.base[l], (size_t)n_susp * (size_t)capl * (size_t)D.rstride * 8) != cudaSuccess ||
+                cudaMalloc(&D.slot[l], szN * 4) != cudaSuccess) {
+                cudaGetLastError();
+                if (ev_ready) cudaEventDestroy(ev_ready);
+                return fail(FLINT_ERROR_MEMALLOC, "dense-output storage does not fit in device memory");
+            }
+            D.cap[l] = capl; D.rows[l] = n_susp; D.nlev = l + 1;
+            if (!cuda_ok(cudaMemsetAsync(D.slot[l], 0xFF, szN * 4, s), "dense slots") ||
+                !cuda_ok(flint::launch_dense_slots(D.slot[l], listCD[ovf], n_susp, s), "dense slots")) { le = cudaErrorUnknown; break; }
+            g_launches += 1;
+            c.dv = D.view(); c.dense_avail = c.dv.capacity();
+            const int* in = listCD[ovf];
+            const unsigned long long* n_in = ctr + 4 + ovf;
+            ovf ^= 1;
+            c.ovf_list = listCD[ovf]; c.n_ovf = ctr + 4 + ovf;
+            /* re-arm: work counter, both parked counts, the other suspended count (the plane flag keeps its value) */
+            if (!cuda_ok(cudaMemsetAsync(ctr, 0, 24, s), "work counters") || !cuda_ok(cudaMemsetAsync(ctr + 4 + ovf, 0, 8, s), "work counters")) { le = cudaErrorUnknown; break; }
+            le = sweep(in, n_in, n_susp);
         }
-        if (le == cudaSuccess && dense) {                      /* coefficients of the logged steps (erk_kernel.cuh: erk_dense_kernel) */
+        if (le == cudaSuccess && dense && me->dense.kind_coef) {   /* coefficient records from the logged steps (erk_kernel.cuh: erk_dense_kernel) */
+            c.dvo = c.dv; c.dense_eval = 0;
+            int* zf = c.zflag;
             c.zflag = (try_plane && ke->dense_plane) ? (int*)(ctr + 3) : nullptr;
             if (c.zflag) { le = ke->dense_plane(c, grid_all, 128, s); g_launches += 1; }
             if (le == cudaSuccess) { le = ke->dense_coeffs(c, grid_all, 128, s); g_launches += 1; }
+            c.zflag = zf;
+        }
+        if (dense) {                                           /* Interpolate runs the dense kernels again (fused path): keep the plane flag */
+            me->dense_plane_ok = try_plane && ke->dense_plane;
+            if (le == cudaSuccess && me->dense_plane_ok && !cuda_ok(cudaMemcpyAsync(me->dense.dzflag, ctr + 3, 4, cudaMemcpyDeviceToDevice, s), "plane flag")) le = cudaErrorUnknown;
         }
         if (e1) cudaEventRecord(e1, s);
-        if (!cuda_ok(le, "kernel launch")) { if (ev_ready) cudaEventDestroy(ev_ready); return FLINT_ERROR; }
+        if (le != cudaSuccess) {                               /* cudaErrorUnknown: a step above failed and left its own message */
+            if (le != cudaErrorUnknown || g_last_error.empty()) cuda_ok(le, "kernel launch");
+            if (ev_ready) cudaEventDestroy(ev_ready);
+            return FLINT_ERROR;
+        }
 
         if (ex.host) {
             bool ok = copy2d(xf, c.xf, 8, 1, false, "D2H xf", s) && copy2d(yf, c.yf, 8, n, false, "D2H yf", s);
@@ -743,7 +867,7 @@ static ExecCtx make_exec(const flint_exec* x)
     if (x) {
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
-        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline; e.round_len = x->round_len;
+        e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline; e.round_len = x->round_len; e.dense_mode = x->dense_mode;
         e.n_devices = x->n_devices; e.shard_chunk = x->shard_chunk > 0 ? x->shard_chunk : FLINT_SHARD_CHUNK;
         for (int k = 0; k < FLINT_MAX_DEVICES; ++k) e.devices[k] = x->devices[k];
     }
@@ -884,15 +1008,16 @@ extern "C" int flint_erk_integrate(flint_erk_t* me, double x0, const double* y0,
 
 /* ------------------------------------------------------------------ Interpolate */
 static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* yarr, int layout, int* status,
-                            bool has_save, bool save, const ExecCtx& ex, bool scalar_call, const Shard* shard_in = nullptr)
+                            bool has_save, bool save, const ExecCtx& ex, bool scalar_call, const Shard* shard_in = nullptr,
+                            bool per_traj = false)
 {
     if (!me->interp_on) return me->status = FLINT_ERROR_INTP_OFF;                       /* src/ERKInterp.f90:45-48 */
     const bool dealloc = has_save ? !save : true;                                        /* :52-53 */
     if (G < 1) return me->status;                                                        /* :56-57 */
     DenseStore& D = me->dense;
-    if (!D.dxint || D.N <= 0) return me->status = FLINT_ERROR_INTP_OFF;                  /* storage already freed */
+    if (!D.allocated() || D.N <= 0) return me->status = FLINT_ERROR_INTP_OFF;            /* storage already freed */
     if (scalar_call && !(me->dense_is_scalar && D.N == 1))     /* the scalar Interpolate reads the dense output of a scalar Integrate */
-        return me->status = fail(FLINT_ERROR_INTP_OFF, "flint_erk_interpolate: the stored dense output belongs to a batch Integrate; use flint_erk_interpolate_batch");
+        return fail(FLINT_ERROR_INTP_OFF, "flint_erk_interpolate: the stored dense output belongs to a batch Integrate; use flint_erk_interpolate_batch");   /* the object's status is untouched */
     if (!xarr || !yarr) return me->status = fail(FLINT_ERROR_PARAMS, "xarr and yarr are required");
     if (!cuda_ok(cudaSetDevice(D.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const long N = D.N;
@@ -901,22 +1026,28 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     cudaStream_t s = ex.stream;
     ScopedCache scoped;                      /* Yarr can be most of the device memory: not kept between calls */
     DevBuf scratch(scoped, D.device);
-    /* monotonicity of the shared grid is a host-side check (:60-68) */
-    std::vector<double> hx;
-    const double* xh = xarr;
-    if (!ex.host) { hx.resize((size_t)G); if (!cuda_ok(cudaMemcpy(hx.data(), xarr, (size_t)G * 8, cudaMemcpyDeviceToHost), "D2H xarr")) return me->status = FLINT_ERROR; xh = hx.data(); }
+    const size_t nx = per_traj ? (size_t)N * (size_t)G : (size_t)G;
+    /* monotonicity of a shared grid is a host-side check (:60-68); per-trajectory grids are checked on the device */
     int up = 1, down = 1;
-    for (long i = 0; i + 1 < G; ++i) { if (!(xh[i] < xh[i + 1])) up = 0; if (!(xh[i] > xh[i + 1])) down = 0; }
+    if (!per_traj) {
+        std::vector<double> hx;
+        const double* xh = xarr;
+        if (!ex.host) { hx.resize((size_t)G); if (!cuda_ok(cudaMemcpy(hx.data(), xarr, (size_t)G * 8, cudaMemcpyDeviceToHost), "D2H xarr")) return me->status = FLINT_ERROR; xh = hx.data(); }
+        for (long i = 0; i + 1 < G; ++i) { if (!(xh[i] < xh[i + 1])) up = 0; if (!(xh[i] > xh[i + 1])) down = 0; }
+    }
     flint::InterpArgs a{};
-    a.N = N; a.G = G; a.nI = D.nI; a.pstar = D.pstar; a.cap = D.cap; a.dxint = D.dxint; a.dbip = D.dbip; a.dcount = D.dcount; a.rstride = D.rstride;
+    a.N = N; a.G = G; a.nI = D.nI; a.pstar = D.pstar; a.dv = D.view(); a.dcount = D.dcount; a.per_traj = per_traj ? 1 : 0;
     a.layout = layout; a.fma = me->arith == FLINT_ARITH_FMA;
     const size_t ny = (size_t)N * (size_t)G * (size_t)D.nI;
     double* d_y = nullptr; int* d_st = nullptr;
     if (ex.host) {
-        double* d_x = scratch.alloc<double>((size_t)G);
+        double* d_x = scratch.alloc<double>(nx);
         d_y = scratch.alloc<double>(ny); d_st = scratch.alloc<int>((size_t)N);
         if (!d_x || !d_y || !d_st) return me->status = fail(FLINT_ERROR_MEMALLOC, "device allocation failed");
-        if (!cuda_ok(cudaMemcpyAsync(d_x, xarr, (size_t)G * 8, cudaMemcpyHostToDevice, s), "H2D xarr")) return me->status = FLINT_ERROR;
+        /* a per-trajectory grid of a sharded call: this shard's rows of xarr[Ntot][G] */
+        const bool okx = per_traj ? shard_copy(sh, N, 0, N, d_x, xarr, (size_t)G * 8, 1, true, "H2D xarr", s)
+                                  : cuda_ok(cudaMemcpyAsync(d_x, xarr, (size_t)G * 8, cudaMemcpyHostToDevice, s), "H2D xarr");
+        if (!okx) return me->status = FLINT_ERROR;
         a.xarr = d_x; a.yarr = d_y; a.status = d_st;
     } else {
         a.xarr = xarr; a.yarr = yarr; a.status = status;
@@ -924,8 +1055,56 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.device);
-    if (!cuda_ok(flint::launch_interp(a, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
-    g_launches += 2;
+    if (D.kind_coef) {                                       /* coefficient records: the evaluation kernels (interp_kernel.cu) */
+        if (!cuda_ok(flint::launch_interp(a, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
+        g_launches += 2;
+    } else {
+        /* step logs: erk_dense_kernel rebuilds every step's coefficients in registers and (layout 0) evaluates the grid from
+         * there -- the fused path; for [nI][G][N] it writes them to a temporary coefficient store first */
+        const flint_sys& sys = *me->sys;
+        const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, me->events_on);
+        if (!ke) ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, false);
+        if (!ke) return me->status = fail(FLINT_ERROR, "no kernel compiled for this method / system");
+        if (!cuda_ok(flint::launch_interp_validate(a, up, down, s), "interp validate")) return me->status = FLINT_ERROR;
+        g_launches += 1;
+        KArgs c{};
+        fill_static_kargs(me, c);
+        c.N = N;
+        ke->load_coefficients(c.coef);
+        flint::det_pow_constants(c.powc);
+        c.dv = a.dv; c.dense_count = D.dcount;
+        c.zflag = me->dense_plane_ok ? D.dzflag : nullptr;
+        DenseStore T;                                        /* temporary coefficient records ([nI][G][N] output) */
+        struct Guard { DenseStore& t; ~Guard() { t.release(); } } guard{T};
+        if (layout == 0) {
+            c.dense_eval = 1; c.dvo = c.dv;
+            c.ix = a.xarr; c.iy = a.yarr; c.iG = G; c.ix_per_traj = a.per_traj; c.istatus = a.status;
+        } else {
+            T.device = D.device; T.N = N; T.n = D.n; T.nI = D.nI; T.pstar = D.pstar; T.kind_coef = true; T.nlev = D.nlev;
+            T.rstride = D.nI * (D.pstar + 1) + 3; T.rstride += T.rstride & 1;
+            for (int l = 0; l < D.nlev; ++l) {
+                T.cap[l] = D.cap[l]; T.rows[l] = D.rows[l];
+                if (cudaMalloc(&T.base[l], (size_t)T.rows[l] * (size_t)T.cap[l] * (size_t)T.rstride * 8) != cudaSuccess) {
+                    cudaGetLastError();
+                    return me->status = fail(FLINT_ERROR_MEMALLOC, "no device memory for the coefficient records of a [nI][G][N] Interpolate; use layout 0 or flint_exec.dense_mode = 1");
+                }
+            }
+            flint::DenseView tv = T.view();
+            for (int l = 1; l < D.nlev; ++l) tv.slot[l] = D.slot[l];
+            c.dense_eval = 0; c.dvo = tv;
+        }
+        cudaError_t le = cudaSuccess;
+        if (c.zflag) { le = ke->dense_plane(c, 0, 0, s); g_launches += 1; }
+        if (le == cudaSuccess) { le = ke->dense_coeffs(c, 0, 0, s); g_launches += 1; }
+        if (!cuda_ok(le, "dense kernel launch")) return me->status = FLINT_ERROR;
+        if (layout != 0) {
+            flint::InterpArgs b = a;
+            b.dv = c.dvo;
+            if (!cuda_ok(flint::launch_interp(b, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
+            g_launches += 2;
+            if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;   /* before the temporary store goes */
+        }
+    }
     std::vector<int> hst;
     if (ex.host) {
         hst.resize((size_t)N);
@@ -955,13 +1134,13 @@ extern "C" int flint_erk_interpolate(flint_erk_t* me, const double* xarr, long G
     return interpolate_impl(me, xarr, G, yarr, 0, nullptr, has_save != 0, save_coeffs != 0, ex, true);
 }
 
-extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, long G, double* yarr, int layout, int* status,
-                                           int has_save, int save_coeffs, const flint_exec* exec)
+static int interpolate_batch(flint_erk_t* me, const double* xarr, long G, double* yarr, int layout, int* status,
+                             int has_save, int save_coeffs, const flint_exec* exec, bool per_traj)
 {
     if (!me) return FLINT_ERROR_PARAMS;
     if (layout != 0 && layout != 1) return me->status = fail(FLINT_ERROR_PARAMS, "layout must be 0 or 1");
     const ExecCtx ex = make_exec(exec);
-    if (me->shard_N > 0 && !me->shard.empty() && !me->dense.dxint) {
+    if (me->shard_N > 0 && !me->shard.empty() && !me->dense.allocated()) {
         /* the last Integrate was sharded over devices: every shard interpolates where its dense output lives and writes the
          * caller's (host) Yarr at its trajectories' own offsets */
         if (!ex.host) return me->status = fail(FLINT_ERROR_PARAMS, "the dense output of a sharded Integrate is interpolated into host buffers");
@@ -976,7 +1155,7 @@ extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, 
                 ExecCtx e1 = ex;
                 e1.device = me->shard_device[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0;
                 if (shard_count(sh.Ntot, D, k, sh.chunk) == 0) return;
-                rc[k] = interpolate_impl(me->shard[k], xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, e1, false, &sh);
+                rc[k] = interpolate_impl(me->shard[k], xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, e1, false, &sh, per_traj);
                 if (rc[k] != FLINT_SUCCESS) err[k] = g_last_error;
             });
         for (auto& t : th) t.join();
@@ -986,7 +1165,18 @@ extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, 
         if (dealloc && st == FLINT_SUCCESS) { me->dense_allocated = false; me->shard_N = 0; }
         return me->status = st;
     }
-    return interpolate_impl(me, xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, ex, false);
+    return interpolate_impl(me, xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, ex, false, nullptr, per_traj);
+}
+
+extern "C" int flint_erk_interpolate_batch(flint_erk_t* me, const double* xarr, long G, double* yarr, int layout, int* status,
+                                           int has_save, int save_coeffs, const flint_exec* exec)
+{
+    return interpolate_batch(me, xarr, G, yarr, layout, status, has_save, save_coeffs, exec, false);
+}
+extern "C" int flint_erk_interpolate_batch_grids(flint_erk_t* me, const double* xarr, long G, double* yarr, int layout, int* status,
+                                                 int has_save, int save_coeffs, const flint_exec* exec)
+{
+    return interpolate_batch(me, xarr, G, yarr, layout, status, has_save, save_coeffs, exec, true);
 }
 
 /* ------------------------------------------------------------------ Info (src/ERKInit.f90:346-394) */

@@ -54,6 +54,7 @@
 #endif
 #include "erk_methods_gen.cuh"
 #include "systems.cuh"
+#include "interp_eval.cuh"
 
 namespace flint {
 
@@ -375,77 +376,89 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
     for (int i = 0; i < M; ++i) c.EV1[i] = EV1[i][0];                   /* what `EV0 = EV1` (:550) carries to the next step */
 }
 
-/* ---- dense-output storage (InterpOn), one contiguous run per trajectory (interp_kernel.cu):
- *   dxint[N][cap+1]  Xint;   dbip[N][cap][rstride]  per accepted step Bip(ii,j) as [j][ii], (pstar+1)*nI doubles;
- *   dflag[N][cap]    1 = the slot holds the step's LOG (X, h, Y, F0) and erk_dense_kernel still has to turn it into
- *                    coefficients, 0 = coefficients.
- * The hot loop only logs an accepted step (2n+2 doubles); the extra dense stages and the coefficients are computed
- * afterwards by erk_dense_kernel, one thread per (trajectory, step), by recomputing the step from its log -- the same
- * bits, because F is pure and the arithmetic is the same straight-line code.  Measured before the split (dense stages,
- * coefficients and the 54-double store inside the lane loop): Verner98R 5.2x, DOP853 2.7x slower than without InterpOn. ---- */
+/* ---- dense-output storage (InterpOn): records of a growing store, kargs.h: DenseView.
+ * The hot loop only LOGS an accepted step (2n+2 doubles); the extra dense stages and the coefficients are computed afterwards by
+ * erk_dense_kernel, one thread per (trajectory, step), by recomputing the step from its log -- the same bits, because F is
+ * pure and the arithmetic is the same straight-line code.  Measured before the split (dense stages, coefficients and the
+ * 54-double store inside the lane loop): Verner98R 5.2x, DOP853 2.7x slower than without InterpOn. ---- */
 template <class METHOD, class SYS>
-__device__ __forceinline__ void store_dense_record(const KArgs& p, long idx, int acc, const double (&B)[METHOD::PSTAR + 1][SYS::N])
+__device__ __forceinline__ void store_coef_record(double* __restrict__ rec, int rstride, int nI, const int* istates, double X0, double X1,
+                                                  const double (&B)[METHOD::PSTAR + 1][SYS::N])
 {
     constexpr int N = SYS::N, PS = METHOD::PSTAR;
-    double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)p.dense_rstride;
-    if (p.nI == N) {                   /* all states, in order (the default): the record is B itself */
+    reinterpret_cast<double2*>(rec)[0] = make_double2(X0, X1);        /* records are 16-byte aligned (rstride is even) */
+    double* __restrict__ c = rec + 2;
+    if (nI == N) {                     /* all states, in order (the default): the record is B itself */
         if (((PS + 1) * N) % 2 == 0) {
 #pragma unroll
             for (int q = 0; q < (PS + 1) * N / 2; ++q)
-                reinterpret_cast<double2*>(rec)[q] = make_double2(B[(2 * q) / N][(2 * q) % N], B[(2 * q + 1) / N][(2 * q + 1) % N]);
+                reinterpret_cast<double2*>(c)[q] = make_double2(B[(2 * q) / N][(2 * q) % N], B[(2 * q + 1) / N][(2 * q + 1) % N]);
         } else {
 #pragma unroll
             for (int j = 0; j <= PS; ++j)
 #pragma unroll
-                for (int c = 0; c < N; ++c) rec[j * N + c] = B[j][c];
+                for (int cc = 0; cc < N; ++cc) c[j * N + cc] = B[j][cc];
         }
     } else {
         for (int j = 0; j <= PS; ++j)
-            for (int ii = 0; ii < p.nI; ++ii) {
+            for (int ii = 0; ii < nI; ++ii) {
                 double v = 0.0;
 #pragma unroll
-                for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
-                rec[j * p.nI + ii] = v;
+                for (int cc = 0; cc < N; ++cc) if (istates[ii] - 1 == cc) v = B[j][cc];
+                c[j * nI + ii] = v;
             }
     }
-    p.dflag[idx * p.dense_cap + (acc - 1)] = 0;
+    rec[rstride - 1] = kDenseCoef;
 }
+/* accepted step `acc` (1-based) of the hot loop: X, h, Y, F0.  A call that cannot grow the store drops what does not fit
+ * (Interpolate then reports FLINT_ERROR_INTP_ARRAY for that trajectory); every other call suspends the trajectory first. */
 template <class SYS>
 __device__ __forceinline__ void log_dense_step(const KArgs& p, long idx, int acc, double X, double h, const double (&Y)[SYS::N], const double (&F0)[SYS::N])
 {
     constexpr int N = SYS::N;
-    if (acc > p.dense_cap) return;
-    p.dxint[idx * (p.dense_cap + 1) + acc] = X + h;
-    double* __restrict__ rec = p.dbip + (idx * p.dense_cap + (acc - 1)) * (long)p.dense_rstride;    /* rstride is even: 16-byte aligned */
+    if (acc > p.dv.capacity()) return;
+    double* __restrict__ rec = p.dv.rec(idx, acc - 1);
     reinterpret_cast<double2*>(rec)[0] = make_double2(X, h);
 #pragma unroll
     for (int q = 0; q < N / 2; ++q) reinterpret_cast<double2*>(rec)[1 + q] = make_double2(Y[2 * q], Y[2 * q + 1]);
     if (N % 2) rec[2 + N - 1] = Y[N - 1];
 #pragma unroll
     for (int c = 0; c < N; ++c) rec[2 + N + c] = F0[c];
-    p.dflag[idx * p.dense_cap + (acc - 1)] = 1;
+    rec[p.dv.rstride - 1] = kDenseLog;
+}
+/* a step committed by the event code: its end may have been moved to the event (h != h_stage) and Y1 replaced by the event
+ * state (:505-528); the dense stages are then rebuilt with the new h and the old stages (quirk Q6, :507-510,558-562) */
+template <class SYS>
+__device__ __forceinline__ void log_dense_event_step(const KArgs& p, long idx, int acc, double X, double h, const double (&Y)[SYS::N],
+                                                     const double (&F0)[SYS::N], double h_stage, const double (&Y1)[SYS::N])
+{
+    constexpr int N = SYS::N;
+    if (acc > p.dv.capacity()) return;
+    double* __restrict__ rec = p.dv.rec(idx, acc - 1);
+    rec[0] = X; rec[1] = h;
+#pragma unroll
+    for (int c = 0; c < N; ++c) { rec[2 + c] = Y[c]; rec[2 + N + c] = F0[c]; rec[3 + 2 * N + c] = Y1[c]; }
+    rec[2 + 2 * N] = h_stage;
+    rec[p.dv.rstride - 1] = kDenseEvLog;
 }
 
 /* ---- the tail of an accepted step (:555-635): dense store, stale-action quirk, natural-step output,
  * advance, new step size, too-small test.  Shared by the hot path (state in registers) and by the
  * deferred event commit (state in the local-memory context). ---- */
-/* dense_mode (InterpOn only): 1 = store the step's dense coefficients B now (steps committed by the event code),
- * 2 = the step was logged for erk_dense_kernel (hot path), 0 = InterpOn is off. */
+/* dense_mode (InterpOn only): 1 = log the step here as an event-committed step (h_stage = the step size its stages were
+ * computed with), 2 = the hot path has logged it already, 0 = InterpOn is off. */
 template <class METHOD, class SYS, bool FMA, bool EVENTS>
 __device__ __forceinline__ void commit_tail(const KArgs& p, long idx, int dense_mode, bool eventsOn, int evAction, double hSign, double hmax,
         double& X, double (&Y)[SYS::N], double (&F0)[SYS::N], double& h_io, double& hbyhoptOld, bool& lastRej, bool LAST, int& st,
         int& fcalls, int acc, double h, double (&Y1)[SYS::N], const double (&F0new)[SYS::N], double Err, double hbyhopt,
-        bool bip_counted, const double (&ENY)[SYS::N], const double (&B)[METHOD::PSTAR + 1][SYS::N], double& powKey, double& powVal)
+        bool bip_counted, const double (&ENY)[SYS::N], double h_stage, double& powKey, double& powVal)
 {
     constexpr int N = SYS::N;
     const long NN = p.N;
     const bool const_step = p.const_step != 0;
     if (dense_mode != 0) {                                              /* :555-566 */
         if (!bip_counted) { fcalls += METHOD::FC_DENSE; bip_counted = true; }
-        if (dense_mode == 1 && acc <= p.dense_cap) {   /* per-trajectory runs: dxint[N][cap+1], dbip[N][cap][rstride] (interp_kernel.cu) */
-            p.dxint[idx * (p.dense_cap + 1) + acc] = X + h;
-            store_dense_record<METHOD, SYS>(p, idx, acc, B);
-        }
+        if (dense_mode == 1) log_dense_event_step<SYS>(p, idx, acc, X, h, Y, F0, h_stage, Y1);
     }
     if (EVENTS && eventsOn) {                                           /* :572-582 (quirks Q4, Q5) */
         const int act = evAction & 0x7f;
@@ -499,14 +512,10 @@ __device__ __noinline__ void deferred_event_commit(const SYS& sys, const KArgs& 
     event_rare_path<METHOD, SYS, FMA>(sys, p, c, idx, hSign);
 #pragma unroll
     for (int i = 0; i < M; ++i) c.EV0[i] = c.EV1[i];                  /* :550 */
-    const bool dense = p.dense_cap > 0;
-    if (dense) {
-        if (c.h != c.h_stage) c.haveB = false;                         /* truncated: rebuild the dense stages (quirk Q6) */
-        remat_bip<METHOD, SYS, FMA>(sys, p, c);
-    }
+    const bool dense = p.dv.nlev > 0;    /* the step is logged with (h, h_stage, Y1): erk_dense_kernel rebuilds its dense stages (quirk Q6) */
     double Xn = c.X, hio = c.h, pk = qnan(), pv = 0.0;
     commit_tail<METHOD, SYS, FMA, true>(p, idx, dense ? 1 : 0, true, c.action, hSign, c.hmax, Xn, c.Y, c.F0old, hio, c.hbyhoptOld, c.lastRej,
-                                               c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.B, pk, pv);
+                                               c.LAST, c.st, c.fcalls, c.acc, c.h, c.Y1, c.F0new, c.Err, c.hbyhopt, c.bip_counted, c.ENY, c.h_stage, pk, pv);
     c.X = Xn; c.h = hio;       /* new X, next step size; new Y in c.Y, new F0 in c.F0old */
 }
 
@@ -616,7 +625,7 @@ __device__ __forceinline__ void store_results(const KArgs& p, long idx, const La
     if (p.stifftest) p.stifftest[idx] = L.stiffOut;
     if (p.ev_count) p.ev_count[idx] = L.evCount;
     if (p.steps_count) p.steps_count[idx] = L.acc + 1;
-    if (p.dense_count) p.dense_count[idx] = L.acc;
+    if (p.dense_count) p.dense_count[idx] = L.acc;       /* allocated(me%Xint): acc + 1 abscissae, acc coefficient sets */
     p.si[SI::FLAGS * p.scap + idx] = kFlagDone;
 }
 template <class SYS> __host__ __device__ constexpr bool is_plane_variant()
@@ -725,7 +734,6 @@ __global__ void __launch_bounds__(128) erk_init_kernel(const __grid_constant__ K
 #pragma unroll
         for (int c = 0; c < N; ++c) p.yint[((long)c * p.steps_cap + 0) * NN + idx] = L.Y[c];
     }
-    if (p.dense_cap > 0) p.dxint[idx * (p.dense_cap + 1)] = L.X;            /* :259 */
     if (!keeps_going<SYS>(p, L)) store_results<SYS>(p, idx, L);
     else state_store<SYS>(p, idx, L, 0);
 }
@@ -929,6 +937,13 @@ erk_step_kernel(const __grid_constant__ KArgs p)
             if (!keeps_going<SYS>(p, L)) { store_results<SYS>(p, idx, L); have = false; }
         }
 
+        /* ---------------- InterpOn: every level of the dense store full -> suspend; the host adds a level and resumes ---------------- */
+        if (have && p.dv.nlev > 0 && L.acc >= p.dense_avail && !(EVMODE == 1 && pending)) {
+            state_store<SYS>(p, idx, L, 0);
+            p.ovf_list[atomicAdd(p.n_ovf, 1ULL)] = (int)idx;
+            have = false;
+            if (GANG) key[jloc] = 2.0f;
+        }
         /* ---------------- one step attempt for every lane that owns a trajectory (:263-637) ---------------- */
         if (have) {
             if (L.hSign * (madd<FMA>(fac, L.h, L.X) - L.Xf) > 0.0) { L.h = L.Xf - L.X; L.LAST = true; }   /* :268-271 */
@@ -1027,23 +1042,14 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                     }
                 }
                 if (!rare) {
-                    double B[PS + 1][N];       /* unused when the step is logged for erk_dense_kernel */
-                    const bool dense = p.dense_cap > 0;
-                    int dense_mode = 0;
-                    if (dense) {
-                        if constexpr (METHOD::FC_DENSE == 0) {      /* no extra stages (DOP54): the coefficients are cheaper than a recomputation */
-                            METHOD::template dense_coeffs<SYS, FMA>(ks, L.Y, h, Ynew, B, p.coef);
-                            dense_mode = 1;
-                        } else {
-                            log_dense_step<SYS>(p, idx, L.acc, L.X, h, L.Y, L.F0);
-                            dense_mode = 2;
-                        }
-                    }
+                    const bool dense = p.dv.nlev > 0;
+                    if (dense) log_dense_step<SYS>(p, idx, L.acc, L.X, h, L.Y, L.F0);     /* :555-566; coefficients: erk_dense_kernel */
+                    const int dense_mode = dense ? 2 : 0;
                     double hio = h, F0new[N];
                     ks.template load<METHOD::SLOT_F0NEW>(F0new);
                     commit_tail<METHOD, SYS, FMA, EVENTS>(p, idx, dense_mode, L.eventsOn, L.evAction, L.hSign, L.hmax, L.X, L.Y, L.F0, hio, L.hbyhoptOld,
                                                           L.lastRej, L.LAST, L.st, L.fcalls, L.acc, h, Ynew, F0new, Err, hbyhopt,
-                                                          bip_counted, Ynew, B, powKey, powVal);
+                                                          bip_counted, Ynew, h, powKey, powVal);
                     L.h = hio;
                 }
             } else {                                                        /* :607-624 */
@@ -1118,50 +1124,113 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
 }
 
 /* ===================================================================== dense output: coefficients from the step logs */
-/* resident CTAs per SM: 3 (168 registers) where the stage set fits them, else 2 -- measured per 2^16 planar CR3BP orbits:
+/* One thread per (trajectory, accepted step); a CTA = 128 consecutive steps of one trajectory (blockIdx.x = trajectory,
+ * blockIdx.y = block of steps), so its logs and its output are contiguous.  Every thread recomputes its step from the log, runs
+ * the extra dense stages and builds the power-basis coefficients in registers (src/ERKStepInt.f90:250-323,473-563,659-700).  Then
+ *   p.dense_eval == 0: the coefficient record is written to p.dvo (in place when dvo is dv);
+ *   p.dense_eval != 0: FUSED Interpolate -- the coefficients go to shared memory and the CTA evaluates the grid points that lie
+ *       in its 128 steps (interp_eval.cuh) straight into Yarr: Bip never exists in HBM (config 4: 58 GB less written and read
+ *       per 2^18 orbits, and a store of 2n+2 instead of (pstar+1)*nI doubles per step).
+ * resident CTAs per SM: 3 (168 registers) where the stage set fits them, else 2 -- measured per 2^16 planar CR3BP orbits:
  * DOP853 26.9 ms (2) / 25.5 (3) / 28.1 (4); Verner98R 27.9 / 30.7 / 38.9 (spills) */
 #ifndef FLINT_DENSE_MIN_BLOCKS
 #define FLINT_DENSE_MIN_BLOCKS(METHOD) ((METHOD::NSLOT) <= 12 ? 3 : 2)
 #endif
+constexpr int kDenseBlock = 128;
+template <class METHOD> __host__ __device__ constexpr int dense_smem_doubles(int nI)
+{
+    const int rs = (METHOD::PSTAR + 1) * nI;
+    return kDenseBlock * (rs + (rs & 1)) + 2 * (kDenseBlock + 2);      /* sB, sX, sG (longs) */
+}
 template <class METHOD, class SYS, bool FMA>
-__global__ void __launch_bounds__(128, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense_kernel(const __grid_constant__ KArgs p)
+__global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense_kernel(const __grid_constant__ KArgs p)
 {
     constexpr int N = SYS::N, PS = METHOD::PSTAR;
     /* plane variant and general kernel launched back to back, like the step kernels: the flag says which one runs.  The
      * plane variant skips the stage sums of the identically +0 components and forms their coefficients from +0 stage
      * values with the general expressions, so the zeros carry the same signs */
     if (p.zflag && ((*p.zflag != 0) != is_plane_variant<SYS>())) return;
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.N) return;
-    int nacc = p.dense_count[t];
-    if (nacc > p.dense_cap) nacc = (int)p.dense_cap;
+    const long t = blockIdx.x;
+    const long ntot = p.dense_count[t];
+    const long nacc = ntot < p.dv.capacity() ? ntot : p.dv.capacity();
+    const long s0 = (long)blockIdx.y * kDenseBlock;
+    if (s0 >= nacc) return;
+    if (p.dense_eval && p.istatus[t] != FLINT_SUCCESS) return;       /* this trajectory's grid failed the validation (:60-76) */
+    const int ns = (int)(nacc - s0 < kDenseBlock ? nacc - s0 : kDenseBlock);
+    const int tid = threadIdx.x;
+    extern __shared__ double dsm[];
+    const int rs = (PS + 1) * p.nI, rsp = rs + (rs & 1);
+    double* sB = dsm;                                       /* [128][rsp] */
+    double* sX = dsm + kDenseBlock * rsp;                   /* [129] (+1 pad) */
+    long* sG = reinterpret_cast<long*>(sX + kDenseBlock + 2);   /* [129] */
     SYS sys;
     sys_load(sys, p);
-    for (int s = blockIdx.y; s < nacc; s += gridDim.y) {
-        /* with two warps per sub-partition every DRAM round trip is exposed (ncu: a quarter of all stall samples sat on the
-         * flag test and on the first use of the log): flag and log are requested together, and the next step's lines are
-         * pulled into L2 while this one is computed */
-        const unsigned char flag = p.dflag[t * p.dense_cap + s];     /* 0: written by the event code */
-        const double* __restrict__ rec = p.dbip + (t * p.dense_cap + s) * (long)p.dense_rstride;
-        double lg[2 * N + 2];
+    if (tid < ns) {
+        const double* __restrict__ rec = p.dv.rec(t, s0 + tid);
+        const double kind = rec[p.dv.rstride - 1];
+        const double X = rec[0], h = rec[1];                /* a coefficient record: X0, X1 */
+        if (kind == kDenseCoef) {                           /* built by an earlier pass */
+            if (p.dense_eval) {
+                sX[tid] = X; if (tid == ns - 1) sX[ns] = h;
+                for (int q = 0; q < rs; ++q) sB[tid * rsp + q] = rec[2 + q];
+            } else if (p.dvo.base[0] != p.dv.base[0]) {
+                double* __restrict__ o = p.dvo.rec(t, s0 + tid);
+                o[0] = X; o[1] = h;
+                for (int q = 0; q < rs; ++q) o[2 + q] = rec[2 + q];
+                o[p.dvo.rstride - 1] = kDenseCoef;
+            }
+        } else {
+            double Y[N], F0[N], Y1[N], Yn[N], Yp[N], e, B[PS + 1][N];
 #pragma unroll
-        for (int c = 0; c < 2 * N + 2; ++c) lg[c] = rec[c];
-        if (s + (int)gridDim.y < nacc) {
-            const long sn = t * p.dense_cap + s + gridDim.y;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dbip + sn * (long)p.dense_rstride));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dbip + sn * (long)p.dense_rstride + 8));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dflag + sn));
+            for (int c = 0; c < N; ++c) { Y[c] = rec[2 + c]; F0[c] = rec[2 + N + c]; }
+            double h_stage = h;
+            const bool ev = kind == kDenseEvLog;
+            if (ev) {
+                h_stage = rec[2 + 2 * N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) Y1[c] = rec[3 + 2 * N + c];
+            }
+            KStore<METHOD, SYS, 0u> ks;
+            ks.s = nullptr;
+            METHOD::template step<SYS, FMA, true, false>(sys, X, Y, F0, h_stage, h, ks, Yn, Yp, p.tol, false, e, p.coef);
+            if (!ev) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) Y1[c] = Yn[c];
+            }
+            METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Y1, B, p.coef);
+            if (p.dense_eval) {
+                sX[tid] = X; if (tid == ns - 1) sX[ns] = X + h;              /* Xint(j+1) = X + h (:555-566) */
+                if (p.nI == N) {
+#pragma unroll
+                    for (int j = 0; j <= PS; ++j)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) sB[tid * rsp + j * N + c] = B[j][c];
+                } else {
+                    for (int j = 0; j <= PS; ++j)
+                        for (int ii = 0; ii < p.nI; ++ii) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
+                            sB[tid * rsp + j * p.nI + ii] = v;
+                        }
+                }
+            } else store_coef_record<METHOD, SYS>(p.dvo.rec(t, s0 + tid), p.dvo.rstride, p.nI, p.istates, X, X + h, B);
         }
-        if (flag == 0) continue;
-        const double X = lg[0], h = lg[1];
-        double Y[N], F0[N], Yn[N], Yp[N], e, B[PS + 1][N];
-#pragma unroll
-        for (int c = 0; c < N; ++c) { Y[c] = lg[2 + c]; F0[c] = lg[2 + N + c]; }
-        KStore<METHOD, SYS, 0u> ks;
-        ks.s = nullptr;
-        METHOD::template step<SYS, FMA, true, false>(sys, X, Y, F0, h, h, ks, Yn, Yp, p.tol, false, e, p.coef);
-        METHOD::template dense_coeffs<SYS, FMA>(ks, Y, h, Yn, B, p.coef);
-        store_dense_record<METHOD, SYS>(p, t, s + 1, B);
+    }
+    if (!p.dense_eval) return;
+    __syncthreads();
+    const double hs = sign1(sX[1] - sX[0]);                 /* every step points in the direction of integration */
+    const double* __restrict__ xg = p.ix + (p.ix_per_traj ? t * p.iG : 0L);
+    double* __restrict__ yo = p.iy + t * p.iG * p.nI;
+    const bool first = s0 == 0, last = s0 + ns == ntot;
+    switch (p.nI) {
+    case 1: eval_block_steps<FMA, PS, 1>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 2: eval_block_steps<FMA, PS, 2>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 3: eval_block_steps<FMA, PS, 3>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 4: eval_block_steps<FMA, PS, 4>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 5: eval_block_steps<FMA, PS, 5>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 6: if constexpr (N >= 6) eval_block_steps<FMA, PS, 6>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    default: break;
     }
 }
 
@@ -1231,18 +1300,20 @@ cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
     erk_event_kernel<METHOD, SYS, FMA><<<grid, block, 0, s>>>(a);
     return cudaGetLastError();
 }
-/* grid = (ceil(N / block), steps handled in parallel per trajectory) */
+/* grid = (trajectories, blocks of 128 steps up to the store's capacity); blocks beyond a trajectory's step count return at once */
 template <class METHOD, class SYS, bool FMA>
-cudaError_t launch_dense(const KArgs& a, int grid, int block, cudaStream_t s)
+cudaError_t launch_dense(const KArgs& a, int /*grid*/, int /*block*/, cudaStream_t s)
 {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long gy = 4L * (sms > 0 ? sms : 148) * 16 * 32 / (a.N > 0 ? a.N : 1);   /* ~4 waves of threads over the device */
+    const long cap = a.dv.capacity();
+    long gy = (cap + kDenseBlock - 1) / kDenseBlock;
     if (gy < 1) gy = 1;
-    if (gy > a.dense_cap) gy = a.dense_cap;
-    if (gy > 4096) gy = 4096;
-    erk_dense_kernel<METHOD, SYS, FMA><<<dim3((unsigned)grid, (unsigned)gy), block, 0, s>>>(a);
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    const int smem = a.dense_eval ? dense_smem_doubles<METHOD>(a.nI) * 8 : 0;
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(erk_dense_kernel<METHOD, SYS, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    erk_dense_kernel<METHOD, SYS, FMA><<<dim3((unsigned)a.N, (unsigned)gy), kDenseBlock, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }

@@ -1,61 +1,59 @@
-/* interp_kernel.cu -- batched ERK_class%Interpolate (src/ERKInterp.f90:28-140).
+/* interp_kernel.cu -- batched ERK_class%Interpolate (src/ERKInterp.f90:28-140) from stored coefficient records.
  *
- * Evaluates the stored dense output of every trajectory on a grid shared by the ensemble.  The phase is
- * HBM-write bound: algorithmic bytes = N*G*nI*8 written (config 4: 62.9 GB per 2^17 orbits) against
- * ~125 fp64 operations per grid point.
+ * Evaluates the dense output of every trajectory on a grid (shared by the ensemble, or one grid per trajectory).  The phase
+ * writes N*G*nI*8 bytes (config 4: 62.9 GB per 2^17 orbits) against ~113 (strict) / ~70 (FMA) fp64 instructions per grid
+ * point, and reads every coefficient record once.
  *
- * Storage written by the step kernel (erk_kernel.cuh, DENSE), one contiguous run per trajectory:
- *   dxint[N][cap+1]                 Xint(1:acc+1)
- *   dbip [N][cap][pstar+1][nI]      Bip(ii, j) of every accepted step, a record of (pstar+1)*nI doubles
- *   dcount[N]                       accepted steps stored
- * so that a thread walking ONE trajectory reads whole 32-byte sectors (the first version kept trajectories
- * innermost and every coefficient read used 8 of the 32 bytes it moved: 110 GB read for 63 GB written).
- *
- * so that a warp working on ONE trajectory reads whole records with coalesced 16-byte loads (the first version kept
- * trajectories innermost and every coefficient read used 8 of the 32 bytes it moved: 110 GB read for 63 GB written).
- *
- * Every grid point gets the reference's step: the smallest j with Xint(j+1) >= x in the direction of integration
- * (the forward cursor of :85-103; a chunk starts with the binary search that returns the same j), then
+ * Storage (kargs.h: DenseView): one record per accepted step, X0, X1, Bip(ii, j) as [j][ii]; the records of a trajectory are
+ * contiguous within a capacity level.  Every grid point gets the reference's step (forward cursor of :85-103) and
  * Y = sum_k B(:,k) * theta**k exactly as InterpY (:124-140; powers in __powidf2 order, arith.cuh).
+ *
+ *   interp_steps_kernel   [N][G][nI] (each trajectory a Fortran Yarr(nI,G)); also [nI][G][N] for small ensembles and grown
+ *                         stores.  A CTA = 128 consecutive steps of one trajectory: their records arrive as ONE bulk copy
+ *                         (cp.async.bulk, completion on an mbarrier) and are evaluated step-major (interp_eval.cuh).
+ *   interp_kernel_soa     [nI][G][N] with >= 4096 trajectories: one THREAD per trajectory, lanes on consecutive trajectories
+ *                         -> coalesced stores, coefficients in registers.
+ * The fused path (Integrate's step logs -> coefficients in registers -> Yarr, no records at all) is erk_dense_kernel
+ * (erk_kernel.cuh); it shares the step-major evaluation.
  */
+#include <cstdint>
 #include "arith.cuh"
 #include "kargs.h"
-
-#ifndef FLINT_INTERP_LDS128
-#define FLINT_INTERP_LDS128 0
-#endif
+#include "interp_eval.cuh"
 
 namespace flint {
 
-/* hs * (X - x) < 0 of the reference's cursor test (:88) for hs = +-1: the sign of an IEEE difference of finite numbers is
- * exact (gradual underflow), so this is X < x for a forward and X > x for a backward integration -- one compare
- * instead of a subtraction, a product and a compare; NaN compares false either way */
-#ifndef FLINT_INTERP_OLDCMP
-#define FLINT_INTERP_OLDCMP 0
-#endif
-__device__ __forceinline__ bool before(double hs, double X, double x)
-{
-    if (FLINT_INTERP_OLDCMP) return hs * (X - x) < 0.0;
-    return hs > 0.0 ? (X < x) : (X > x);
-}
+__device__ __forceinline__ bool before(double hs, double X, double x) { return before_dir(hs, X, x); }
 
-/* per-trajectory validation of the grid (:60-76): strictly monotone in the direction of
- * integration and inside [Xint(1), Xint(acc+1)] */
+/* per-trajectory validation of the grid (:60-76): strictly monotone in the direction of integration and inside
+ * [Xint(1), Xint(acc+1)].  Works on any kind of record (logs or coefficients).  A shared grid's monotonicity is checked once on
+ * the host; a per-trajectory grid is checked here. */
 __global__ void interp_validate_kernel(InterpArgs a, int grid_monotone_up, int grid_monotone_down)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.N) return;
-    const int acc = a.dcount[t];
+    const long acc = a.dcount[t];
     int st = FLINT_SUCCESS;
-    if (acc < 1 || acc > a.cap) st = FLINT_ERROR_INTP_ARRAY;
+    if (acc < 1 || acc > a.dv.capacity()) st = FLINT_ERROR_INTP_ARRAY;       /* nothing stored / steps were dropped */
     else {
-        const double* xi = a.dxint + t * (a.cap + 1);
-        const double xs = xi[0], xe = xi[acc];
+        const double xs = a.dv.rec(t, 0)[0], xe = dense_x1(a.dv.rec(t, acc - 1), a.dv.rstride);
         const double hs = sign1(xe - xs);
-        if (a.G > 1 && ((hs > 0 && !grid_monotone_up) || (hs < 0 && !grid_monotone_down))) st = FLINT_ERROR_INTP_ARRAY;
-        if (hs * (a.xarr[0] - xs) < 0.0 || hs * (a.xarr[a.G - 1] - xe) > 0.0) st = FLINT_ERROR_INTP_ARRAY;
+        const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+        int up = grid_monotone_up, down = grid_monotone_down;
+        if (a.per_traj) {
+            up = 1; down = 1;
+            for (long i = 0; i + 1 < a.G; ++i) { if (!(xg[i] < xg[i + 1])) up = 0; if (!(xg[i] > xg[i + 1])) down = 0; }
+        }
+        if (a.G > 1 && ((hs > 0 && !up) || (hs < 0 && !down))) st = FLINT_ERROR_INTP_ARRAY;
+        if (hs * (xg[0] - xs) < 0.0 || hs * (xg[a.G - 1] - xe) > 0.0) st = FLINT_ERROR_INTP_ARRAY;
     }
     a.status[t] = st;
+}
+cudaError_t launch_interp_validate(const InterpArgs& a, int up, int down, cudaStream_t s)
+{
+    const int vb = 256;
+    interp_validate_kernel<<<(unsigned)((a.N + vb - 1) / vb), vb, 0, s>>>(a, up, down);
+    return cudaGetLastError();
 }
 
 /* ======================================================================================================
@@ -119,9 +117,12 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     if (t >= a.N || g0 >= g1) return;
     if (a.status[t] != FLINT_SUCCESS) return;
     const int acc = a.dcount[t];
-    const double* __restrict__ xi = a.dxint + t * (a.cap + 1);
-    const double* __restrict__ rec0 = a.dbip + t * a.cap * (long)a.rstride;
-    const double hs = sign1(xi[acc] - xi[0]);
+    /* single-level store (launch_interp): the trajectory's records are one contiguous run; Xint(j+1) = X1 of record j-1 */
+    const int rstride = a.dv.rstride;
+    const double* __restrict__ rbase = a.dv.base[0] + t * a.dv.cum[1] * (long)rstride;
+    const double* __restrict__ rec0 = rbase + 2;                                       /* coefficients of step 1 */
+    auto xi_at = [&](int j) -> double { return j == 0 ? rbase[0] : rbase[(long)(j - 1) * rstride + 1]; };
+    const double hs = sign1(xi_at(acc) - xi_at(0));
     /* chunk start: smallest j in [1,acc] (1-based) with hs*(Xint(j+1) - x) >= 0 */
     int loc;
     {
@@ -129,16 +130,17 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
         int lo = 1, hi = acc;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (!before(hs, xi[mid], x) && xi[mid] == xi[mid] && x == x) hi = mid; else lo = mid + 1;
+            const double xm = xi_at(mid);
+            if (!before(hs, xm, x) && xm == xm && x == x) hi = mid; else lo = mid + 1;
         }
         loc = lo;
     }
     double B[PS + 1][NI];
-    double X0 = xi[loc - 1], X1, h;
-    RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * a.rstride, xi + loc);
+    double X0 = xi_at(loc - 1), X1, h;
+    RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * rstride, rbase + (long)(loc - 1) * rstride + 1);
     RecBuf<RS>::take(rb, &B[0][0], X1);                               /* step loc: coefficients and Xint(loc+1) */
     h = X1 - X0;
-    if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * a.rstride, xi + loc + 1);
+    if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * rstride, rbase + (long)loc * rstride + 1);
     for (long g = g0; g < g1; ++g) {
         const double x = xs[g - g0];
         if (loc < acc && before(hs, X1, x)) {                         /* forward cursor (:85-103) */
@@ -146,12 +148,12 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
             X0 = X1;
             RecBuf<RS>::take(rb, &B[0][0], X1);                       /* the record that was on its way */
             if (loc < acc && before(hs, X1, x)) {                     /* several steps between two grid points: walk Xint */
-                do { loc += 1; X0 = X1; X1 = xi[loc]; } while (loc < acc && before(hs, X1, x));
-                RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * a.rstride, xi + loc);
+                do { loc += 1; X0 = X1; X1 = xi_at(loc); } while (loc < acc && before(hs, X1, x));
+                RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * rstride, rbase + (long)(loc - 1) * rstride + 1);
                 RecBuf<RS>::take(rb, &B[0][0], X1);
             }
             h = X1 - X0;
-            if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * a.rstride, xi + loc + 1);
+            if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * rstride, rbase + (long)loc * rstride + 1);
         }
         const double theta = (x - X0) / h;
         double tk[PS + 1];
@@ -191,203 +193,127 @@ static cudaError_t launch_soa_one(const InterpArgs& a, dim3 grid, cudaStream_t s
     interp_kernel_soa<FMA, PS, NI><<<grid, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
-/* ---- the evaluation kernel: one WARP per trajectory, lanes on 32 consecutive grid points ----
- * A thread-per-trajectory walk (the previous version) diverges: each lane changes step every ~G/acc points, so
- * the warp ran the ~100-instruction "load the next step's coefficients" path at almost every point with one
- * or two lanes active (ncu: 24.5 of 32 lanes, +40 % instructions).  With lanes on consecutive points of ONE
- * trajectory the points of a batch span only 1 + 32*acc/G steps; their records are copied once per warp into
- * a small shared-memory ring with coalesced 16-byte loads and read back with LDS, where lanes on the same step
- * broadcast.  A block is 8 warps = 8 trajectories on the same grid batch, so the [nI][G][N] layout can be written
- * as 64-byte rows (8 trajectories x 8 bytes: whole sectors) through a shared-memory transpose. */
-/* one step record, RS doubles, from HBM into a shared-memory ring slot: coalesced 16-byte cp.async by the warp's lanes */
-template <int RS>
-__device__ __forceinline__ void fetch_record(const double* __restrict__ r, double* d, int lane)
+/* ======================================================================================================
+ * interp_steps_kernel: a CTA = up to 128 consecutive accepted steps of ONE trajectory (blockIdx.x = trajectory, blockIdx.y =
+ * block of steps; capacity levels are multiples of 128 steps, so a block never straddles two levels).  Their coefficient
+ * records are contiguous in HBM: one thread arms an mbarrier with the byte count and issues ONE bulk copy (cp.async.bulk,
+ * the TMA engine's 1-D form) into shared memory; the CTA then evaluates step-major with broadcast reads (interp_eval.cuh).
+ * Three CTAs are resident per SM (3 x 58 KB), so one block's copy travels while the others compute.
+ * ====================================================================================================== */
+constexpr int kStepsBlock = 128;       /* steps per CTA */
+constexpr int kStepsThreads = 256;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <bool FMA, int PS, int NI, bool SOA>
+__global__ void __launch_bounds__(kStepsThreads, 3) interp_steps_kernel(InterpArgs a)
 {
-    if (RS % 2 == 0) {
-        if (lane < RS / 2) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + 2 * lane);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r + 2 * lane));
-        }
+    const long t = blockIdx.x;
+    if (a.status[t] != FLINT_SUCCESS) return;                          /* validated before (launch_interp) */
+    const long acc = a.dcount[t];
+    const long s0 = (long)blockIdx.y * kStepsBlock;
+    if (s0 >= acc) return;
+    const int ns = (int)(acc - s0 < kStepsBlock ? acc - s0 : kStepsBlock);
+    const int rstride = a.dv.rstride;
+    extern __shared__ __align__(128) double ssm[];
+    double* sR = ssm;                                                  /* [128][rstride]: the records as they lie in HBM */
+    double* sX = ssm + kStepsBlock * rstride;                          /* [129] (+1 pad) */
+    long* sG = reinterpret_cast<long*>(sX + kStepsBlock + 2);          /* [129] */
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sG + kStepsBlock + 2);
+    const double* __restrict__ src = a.dv.rec(t, s0);
+    const unsigned bytes = (unsigned)ns * (unsigned)rstride * 8u;      /* a multiple of 16: rstride is even */
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sR)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    }
+    __syncthreads();                                                   /* the barrier is initialised before anyone polls it */
+    {
+        unsigned ok = 0;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+        } while (!ok);
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        sX[i] = sR[(long)i * rstride];
+        if (i == ns - 1) sX[ns] = sR[(long)i * rstride + 1];
+    }
+    __syncthreads();
+    const double hs = sign1(sX[1] - sX[0]);
+    const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+    if (!SOA) {
+        eval_block_steps<FMA, PS, NI>(sR + 2, rstride, sX, sG, ns, s0 == 0, s0 + ns == acc, xg, a.G, hs, a.yarr + t * a.G * NI);
     } else {
-        for (int q = lane; q < RS; q += 32) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(d + q);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(r + q));
+        /* [nI][G][N]: the same evaluation with one 8-byte store per state (small ensembles, grown stores) */
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int i = tid; i <= ns; i += blockDim.x) {
+            long g;
+            if (i == 0) g = s0 == 0 ? 0 : grid_count_upto(xg, a.G, hs, sX[0]);
+            else if (i == ns && s0 + ns == acc) g = a.G;
+            else g = grid_count_upto(xg, a.G, hs, sX[i]);
+            sG[i] = g;
         }
+        __syncthreads();
+        for (int i = warp; i < ns; i += nwarps)
+            for (long gb = sG[i]; gb < sG[i + 1]; gb += 32) {
+                const long g = gb + lane;
+                if (g < sG[i + 1]) {
+                    double y[NI];
+                    eval_point_bcast<FMA, PS, NI>(sX[i], sX[i + 1], xg[g], sR + (long)i * rstride + 2, y);
+#pragma unroll
+                    for (int ii = 0; ii < NI; ++ii) a.yarr[((long)ii * a.G + g) * a.N + t] = y[ii];
+                }
+            }
     }
 }
-/* InterpY (src/ERKInterp.f90:124-140) for one point of the step [X0, X1] whose coefficients B[k][ii] sit in shared memory */
+
 template <bool FMA, int PS, int NI>
-__device__ __forceinline__ void eval_point(double X0, double X1, double x, const double* __restrict__ B, double (&y)[NI])
+static cudaError_t launch_steps_one(const InterpArgs& a, cudaStream_t s)
 {
-    const double h = X1 - X0;
-    const double theta = (x - X0) / h;
-    double tk[PS + 1];
-    theta_powers<PS>(theta, tk);
-    if (FLINT_INTERP_LDS128 && NI % 2 == 0) {          /* two coefficients per 16-byte shared-memory read */
-        const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
-#pragma unroll
-        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-            for (int q = 0; q < NI / 2; ++q) {
-                const double2 b = B2[k * (NI / 2) + q];
-                y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
-                y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
-            }
+    const long cap = a.dv.capacity();
+    const long gy = (cap + kStepsBlock - 1) / kStepsBlock;
+    if (gy < 1 || gy > 65535) return cudaErrorInvalidConfiguration;
+    const int smem = (kStepsBlock * a.dv.rstride + 2 * (kStepsBlock + 2) + 2) * 8;
+    const dim3 grid((unsigned)a.N, (unsigned)gy);
+    if (a.layout == 0) {
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(interp_steps_kernel<FMA, PS, NI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        interp_steps_kernel<FMA, PS, NI, false><<<grid, kStepsThreads, smem, s>>>(a);
     } else {
-#pragma unroll
-        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-            for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
-    }
-}
-
-constexpr int kTW = 8;          /* trajectories (warps) per block */
-constexpr int kRing = 8;        /* step records resident (or on their way) per warp */
-constexpr int kAhead = 3;       /* records requested beyond the ones a batch needs: they arrive while it is evaluated */
-constexpr int kWin = 128;       /* Xint entries staged per warp: win[i] = xi[win_lo + i]; refilled when < kWinLow lie ahead */
-constexpr int kWinLow = 48;
-
-template <bool FMA, int PS, int NI>
-__global__ void __launch_bounds__(kTW * 32) interp_kernel(InterpArgs a)
-{
-    constexpr int RS = (PS + 1) * NI;
-    constexpr int RSP = RS + (RS & 1);                  /* ring stride: keeps 16-byte alignment for odd records */
-    constexpr unsigned FULL = 0xffffffffu;
-    __shared__ __align__(16) double s_ring[kTW][kRing][RSP];
-    __shared__ double s_win[kTW][kWin + 1];
-    __shared__ double s_tile[NI][32][kTW];
-    __shared__ int s_active[kTW];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long t0 = (long)blockIdx.x * kTW, t = t0 + warp;
-    const long g0 = (long)blockIdx.y * a.chunk;
-    long g1 = g0 + a.chunk;
-    if (g1 > a.G) g1 = a.G;
-    const bool active = t < a.N && a.status[t] == FLINT_SUCCESS;       /* warp-uniform */
-    if (lane == 0) s_active[warp] = active ? 1 : 0;
-    int acc = 1;
-    const double* __restrict__ xi = a.dxint;
-    const double* __restrict__ rec0 = a.dbip;
-    double hs = 1.0;
-    int loc_base = 1;
-    if (active) {
-        acc = a.dcount[t];
-        xi = a.dxint + t * (a.cap + 1);
-        rec0 = a.dbip + t * a.cap * (long)a.rstride;
-        hs = sign1(xi[acc] - xi[0]);
-        const double x = a.xarr[g0];                                   /* chunk start: smallest j in [1,acc] with hs*(Xint(j+1) - x) >= 0 */
-        int lo = 1, hi = acc;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (!before(hs, xi[mid], x) && xi[mid] == xi[mid] && x == x) hi = mid; else lo = mid + 1;
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(interp_steps_kernel<FMA, PS, NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
         }
-        loc_base = lo;
-    }
-    double* win = s_win[warp];
-    int win_lo = -1;                                                   /* win[i] = xi[win_lo + i] */
-    int ring_lo = 1, ring_hi = 1;                                      /* steps [ring_lo, ring_hi) are resident, step j in slot j % kRing */
-    double xnext = 0.0;
-    if (active) xnext = a.xarr[g0 + lane < g1 ? g0 + lane : g1 - 1];
-    for (long gb = g0; gb < g1; gb += 32) {
-        const long g = gb + lane;
-        const bool valid = g < g1;
-        double y[NI];
-#pragma unroll
-        for (int ii = 0; ii < NI; ++ii) y[ii] = 0.0;
-        if (active) {
-            const double x = xnext;
-            { const long gn = g + 32; xnext = a.xarr[gn < g1 ? gn : g1 - 1]; }     /* next batch's abscissae, one iteration early */
-            bool pending = valid;
-            while (__any_sync(FULL, pending)) {
-                if (win_lo < 0 || loc_base - 1 - win_lo > kWin - kWinLow) {       /* stage Xint(loc_base ..) */
-                    win_lo = loc_base - 1;
-                    __syncwarp();
-                    for (int i = lane; i <= kWin; i += 32) { const int k = win_lo + i; win[i] = xi[k <= acc ? k : acc]; }
-                    __syncwarp();
-                }
-                int j = loc_base;                                      /* forward cursor (:85-103), per lane */
-                bool more = false;
-                if (pending) {
-                    while (j < acc && j - win_lo < kWin && before(hs, win[j - win_lo], x)) j += 1;
-                    more = j < acc && j - win_lo >= kWin && before(hs, win[kWin], x);     /* the window ended before the step was found */
-                }
-                const bool ok = pending && !more && (j - loc_base) < kRing - kAhead;
-                const unsigned okm = __ballot_sync(FULL, ok);
-                if (okm == 0u) {                                       /* many small steps between two points: move on */
-                    const int first = __ffs(__ballot_sync(FULL, pending)) - 1;
-                    loc_base = __shfl_sync(FULL, j, first);            /* > loc_base: the window's end, or a step far ahead */
-                    win_lo = -1;
-                    continue;
-                }
-                const int last = 31 - __clz(okm);
-                const int jmax = __shfl_sync(FULL, j, last);
-                const int jmin = __shfl_sync(FULL, j, __ffs(okm) - 1);
-                /* records of steps jmin..jmax (+ kAhead more) into the ring, asynchronously */
-                if (ring_hi <= jmin || ring_lo > jmin) { ring_lo = jmin; ring_hi = jmin; }
-                const bool had_all = jmax < ring_hi;                   /* everything this pass reads was requested by an earlier pass */
-                int want_hi = jmax + 1 + kAhead;
-                if (want_hi > acc + 1) want_hi = acc + 1;
-                __syncwarp();                                          /* nobody still reads the slots about to be overwritten */
-                for (int sidx = ring_hi; sidx < want_hi; ++sidx) fetch_record<RS>(rec0 + (long)(sidx - 1) * a.rstride, s_ring[warp][sidx % kRing], lane);
-                asm volatile("cp.async.commit_group;");
-                if (want_hi > ring_hi) ring_hi = want_hi;
-                if (ring_hi - ring_lo > kRing) ring_lo = ring_hi - kRing;
-                if (had_all) asm volatile("cp.async.wait_group 1;" ::: "memory");   /* only this pass's look-ahead may still fly */
-                else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                if (ok) {
-                    eval_point<FMA, PS, NI>(win[j - 1 - win_lo], win[j - win_lo], x, s_ring[warp][j % kRing], y);
-                    pending = false;
-                }
-                loc_base = jmax;
-            }
-            if (a.layout == 0 && valid) {
-                double* __restrict__ o = a.yarr + (t * a.G + g) * NI;
-                if (NI % 2 == 0) {
-#pragma unroll
-                    for (int q = 0; q < NI / 2; ++q) reinterpret_cast<double2*>(o)[q] = make_double2(y[2 * q], y[2 * q + 1]);
-                } else {
-#pragma unroll
-                    for (int ii = 0; ii < NI; ++ii) o[ii] = y[ii];
-                }
-            }
-        }
-        if (a.layout != 0) {                                           /* [nI][G][N]: transpose 8 trajectories x 32 points through shared memory */
-#pragma unroll
-            for (int ii = 0; ii < NI; ++ii) s_tile[ii][lane][warp] = y[ii];
-            __syncthreads();
-            const int p = threadIdx.x >> 3, w = threadIdx.x & 7;       /* 8 consecutive threads = 8 consecutive trajectories = 64 bytes */
-            if (gb + p < g1 && t0 + w < a.N && s_active[w]) {
-#pragma unroll
-                for (int ii = 0; ii < NI; ++ii) a.yarr[((long)ii * a.G + gb + p) * a.N + t0 + w] = s_tile[ii][p][w];
-            }
-            __syncthreads();
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-template <bool FMA, int PS>
-static cudaError_t launch_ni(const InterpArgs& a, dim3 grid, cudaStream_t s)
-{
-    switch (a.nI) {
-    case 1: interp_kernel<FMA, PS, 1><<<grid, kTW * 32, 0, s>>>(a); break;
-    case 2: interp_kernel<FMA, PS, 2><<<grid, kTW * 32, 0, s>>>(a); break;
-    case 3: interp_kernel<FMA, PS, 3><<<grid, kTW * 32, 0, s>>>(a); break;
-    case 4: interp_kernel<FMA, PS, 4><<<grid, kTW * 32, 0, s>>>(a); break;
-    case 5: interp_kernel<FMA, PS, 5><<<grid, kTW * 32, 0, s>>>(a); break;
-    case 6: interp_kernel<FMA, PS, 6><<<grid, kTW * 32, 0, s>>>(a); break;
-    default: return cudaErrorInvalidValue;
+        interp_steps_kernel<FMA, PS, NI, true><<<grid, kStepsThreads, smem, s>>>(a);
     }
     return cudaGetLastError();
 }
+template <bool FMA, int PS>
+static cudaError_t launch_steps_ni(const InterpArgs& a, cudaStream_t s)
+{
+    switch (a.nI) {
+    case 1: return launch_steps_one<FMA, PS, 1>(a, s);
+    case 2: return launch_steps_one<FMA, PS, 2>(a, s);
+    case 3: return launch_steps_one<FMA, PS, 3>(a, s);
+    case 4: return launch_steps_one<FMA, PS, 4>(a, s);
+    case 5: return launch_steps_one<FMA, PS, 5>(a, s);
+    case 6: return launch_steps_one<FMA, PS, 6>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
 template <bool FMA>
-static cudaError_t launch_ps(const InterpArgs& a, dim3 grid, cudaStream_t s)
+static cudaError_t launch_steps_ps(const InterpArgs& a, cudaStream_t s)
 {
     switch (a.pstar) {                         /* DOP54 4, Verner65E 5, DOP853 7, Verner98R 8 */
-    case 4: return launch_ni<FMA, 4>(a, grid, s);
-    case 5: return launch_ni<FMA, 5>(a, grid, s);
-    case 7: return launch_ni<FMA, 7>(a, grid, s);
-    case 8: return launch_ni<FMA, 8>(a, grid, s);
+    case 4: return launch_steps_ni<FMA, 4>(a, s);
+    case 5: return launch_steps_ni<FMA, 5>(a, s);
+    case 7: return launch_steps_ni<FMA, 7>(a, s);
+    case 8: return launch_steps_ni<FMA, 8>(a, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -420,9 +346,10 @@ static cudaError_t launch_soa_ps(const InterpArgs& a, dim3 grid, cudaStream_t s)
 cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, cudaStream_t s)
 {
     InterpArgs a = a0;
-    const int vb = 256;
-    interp_validate_kernel<<<(unsigned)((a.N + vb - 1) / vb), vb, 0, s>>>(a, up, down);
-    if (a.layout != 0 && a.N >= 4096) {       /* structure-of-arrays output and enough trajectories to fill the device with threads */
+    const cudaError_t ev = launch_interp_validate(a, up, down, s);
+    if (ev != cudaSuccess) return ev;
+    /* structure-of-arrays output, enough trajectories to fill the device with threads, one shared grid, records in one run */
+    if (a.layout != 0 && a.N >= 4096 && a.dv.nlev == 1 && !a.per_traj) {
         const long want_t = (long)sm_count * 16 * 32;
         long nc = (want_t + a.N - 1) / a.N;
         const long min_nc = (a.G + FLINT_INTERP_CHUNK - 1) / FLINT_INTERP_CHUNK;
@@ -435,17 +362,7 @@ cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, 
             return a.fma ? launch_soa_ps<true>(a, grid1, s) : launch_soa_ps<false>(a, grid1, s);
         }
     }
-    /* one warp per (trajectory, chunk of the grid): at least ~32 warps per SM in flight when N alone does not give them */
-    const long want = (long)sm_count * 32;
-    long nch = (want + a.N - 1) / a.N;
-    const long max_nch = (a.G + 31) / 32;
-    if (nch > max_nch) nch = max_nch;
-    if (nch > 65535) nch = 65535;
-    if (nch < 1) nch = 1;
-    a.chunk = ((a.G + nch - 1) / nch + 31) / 32 * 32;
-    a.nchunks = (int)((a.G + a.chunk - 1) / a.chunk);
-    dim3 grid((unsigned)((a.N + kTW - 1) / kTW), (unsigned)a.nchunks);
-    return a.fma ? launch_ps<true>(a, grid, s) : launch_ps<false>(a, grid, s);
+    return a.fma ? launch_steps_ps<true>(a, s) : launch_steps_ps<false>(a, s);
 }
 
 }  // namespace flint

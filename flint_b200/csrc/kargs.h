@@ -37,7 +37,39 @@
 
 #define FLINT_NCOEF 256                /* capacity of KArgs::coef (largest pool: Verner98R, 254 values) */
 
+#define FLINT_DENSE_LEVELS 6          /* capacity levels of the dense-output store (each 4x the one before) */
+
 namespace flint {
+
+/* ---- dense-output storage (InterpOn; src/ERKIntegrate.f90:555-566,660-676; src/ERKInit.f90:321-332).
+ * The reference sizes Xint/Bip for MaxSteps + 1 per object; for an ensemble that is N * MaxSteps records, so the store grows on
+ * demand instead: level 0 holds cap_0 steps for every trajectory; a trajectory that fills its levels is suspended (state block),
+ * the host adds a level 4x as deep for exactly the suspended ones and resumes them (capi.cu).  No trajectory ever loses a step.
+ * One RECORD per accepted step, `rstride` doubles (even), rec[rstride-1] = its kind:
+ *   kDenseLog    the step as the hot loop left it: X, h, Y(n), F0(n)                        -- 2n+2 doubles
+ *   kDenseEvLog  a step committed by the event code (possibly truncated, quirk Q6): the above + h_stage, Y1(n)  -- 3n+3 doubles
+ *   kDenseCoef   X0, X1, Bip(ii, j) as [j][ii]: (pstar+1)*nI + 2 doubles (erk_dense_kernel turns logs into this, or evaluates
+ *                the grid points of the step straight from registers and never stores it: the fused Interpolate)
+ * Xint(j+1) of the reference is X0 of record j (and X1 = X + h of the last one): there is no separate Xint array. ---- */
+constexpr double kDenseCoef = 0.0, kDenseLog = 1.0, kDenseEvLog = 2.0;
+struct DenseView {
+    int nlev;                                   /* levels in use; 0 = InterpOn is off */
+    int rstride;                                /* doubles per record */
+    long cum[FLINT_DENSE_LEVELS + 1];           /* steps held below level l: cum[0] = 0, cum[l+1] = cum[l] + cap_l */
+    double* base[FLINT_DENSE_LEVELS];           /* level l: [rows_l][cap_l][rstride] */
+    const int* slot[FLINT_DENSE_LEVELS];        /* level l >= 1: row of trajectory t in that level (-1: none); level 0: row = t */
+    /* record of accepted step a (0-based) of trajectory t; a < cum[nlev] */
+    __host__ __device__ __forceinline__ double* rec(long t, long a) const
+    {
+        int l = 0;
+        while (l + 1 < nlev && a >= cum[l + 1]) ++l;
+        const long row = l == 0 ? t : (long)slot[l][t];
+        return base[l] + (row * (cum[l + 1] - cum[l]) + (a - cum[l])) * (long)rstride;
+    }
+    __host__ __device__ __forceinline__ long capacity() const { return nlev > 0 ? cum[nlev] : 0; }
+};
+/* end abscissa of a record, whatever its kind */
+__host__ __device__ __forceinline__ double dense_x1(const double* r, int rstride) { return r[rstride - 1] == kDenseCoef ? r[1] : r[0] + r[1]; }
 
 /* ATol/RTol as Init stores them (scalar or per-component; src/ERKInit.f90:76-87) */
 struct Tol {
@@ -76,8 +108,17 @@ struct KArgs {
     int* stifftest;              /* [N] in/out or NULL */
     long ev_cap; int* ev_count; double* ev_rec;          /* [(n+2)][cap][N] */
     int steps_on; long steps_cap; double* xint; double* yint; int* steps_count;   /* IntStepsOn output */
-    long dense_cap; double* dxint; double* dbip; int* dense_count; int nI; int istates[FLINT_MAX_N];   /* InterpOn storage */
-    int dense_rstride; unsigned char* dflag;     /* doubles per step slot (>= (pstar+1)*nI and >= 2n+2, even); slot holds a log (1) or coefficients (0) */
+    /* InterpOn storage */
+    DenseView dv;                                /* where accepted steps are logged */
+    long dense_avail;                            /* a trajectory is suspended when it has this many accepted steps (= dv.capacity(), or
+                                                    huge for calls that cannot grow the store: those drop the records beyond it) */
+    int* dense_count;                            /* [N] accepted steps logged */
+    int* ovf_list; unsigned long long* n_ovf;    /* trajectories suspended because their levels are full */
+    int nI; int istates[FLINT_MAX_N];
+    /* erk_dense_kernel: coefficient records are written to dvo (may equal dv: in place); fused Interpolate (dense_eval != 0):
+     * the grid ix[G] (per trajectory: ix[N][G]) is evaluated into iy[N][G][nI] straight from the coefficients in registers */
+    DenseView dvo;
+    int dense_eval, ix_per_traj; long iG; const double* ix; double* iy; const int* istatus;
     /* trajectory state block + work lists (erk_kernel.cuh) */
     double* sd; int* si; long scap;              /* [fields][scap] */
     const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */
@@ -95,16 +136,19 @@ struct KArgs {
 struct InterpArgs {
     long N, G;
     int nI, pstar;
-    long cap;
-    const double* dxint; const double* dbip; const int* dcount;
-    int rstride;                     /* doubles per step slot in dbip */
-    const double* xarr;
+    DenseView dv;                    /* coefficient records (kDenseCoef) */
+    const int* dcount;
+    const double* xarr; int per_traj; /* grid: xarr[G] shared, or xarr[N][G] */
     double* yarr; int layout;        /* 0: [N][G][nI], 1: [nI][G][N] */
     int* status;                     /* [N] */
     int fma;
     long chunk; int nchunks;         /* filled by launch_interp */
 };
 cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
+/* per-trajectory validation of the grid (src/ERKInterp.f90:60-76) against any kind of records */
+cudaError_t launch_interp_validate(const InterpArgs&, int grid_up, int grid_down, cudaStream_t);
+/* slot[list[j]] = j for j < n: rows of a new level of the dense store (registry.cu) */
+cudaError_t launch_dense_slots(int* slot, const int* list, long n, cudaStream_t);
 cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
                                 unsigned long long c3, cudaStream_t);   /* registry.cu */
 

@@ -38,6 +38,17 @@ cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, 
     return cudaGetLastError();
 }
 
+__global__ void dense_slots_kernel(int* slot, const int* __restrict__ list, long n)
+{
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) slot[list[j]] = (int)j;
+}
+cudaError_t launch_dense_slots(int* slot, const int* list, long n, cudaStream_t s)
+{
+    dense_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(slot, list, n);
+    return cudaGetLastError();
+}
+
 }  // namespace flint
 
 extern "C" int flint_b200_kernel_count(void) { return flint::kernel_count(); }

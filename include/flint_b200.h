@@ -144,7 +144,9 @@ typedef struct {
     int device;         /* CUDA device ordinal */
     void* stream;       /* cudaStream_t or NULL (default stream); the call is synchronous unless async != 0 */
     int async;          /* FLINT_MEM_DEVICE only: return after enqueueing; caller synchronises the stream */
-    long dense_cap;     /* dense-output steps stored per trajectory when InterpOn (0 = MaxSteps, as the reference) */
+    long dense_cap;     /* InterpOn: accepted steps the first level of the dense store holds per trajectory (0 = what a third of
+                           the free device memory holds, at most MaxSteps).  Not a limit: trajectories that need more are
+                           suspended, given a deeper level and resumed (synchronous calls; an async call keeps what fits) */
     int block_threads;  /* 0 = the kernel's own CTA size (a property of the system, 128..512); a smaller multiple of 32 lowers it */
     int blocks_per_sm;  /* 0 = as many CTAs per SM as are resident; a smaller number lowers it (tuning experiments) */
     int event_mode;     /* how accepted steps with an event to locate are handled: 0 = automatic, 1 = inside the
@@ -166,6 +168,11 @@ typedef struct {
                            path.  0 / 1 = the single `device`.  Results are identical to the one-device call. */
     int devices[FLINT_MAX_DEVICES];
     long shard_chunk;   /* trajectories per dealt chunk; 0 = FLINT_SHARD_CHUNK */
+    int dense_mode;     /* InterpOn: what Integrate keeps per accepted step.  0 / 2 = the step's log (2n+2 doubles): Interpolate
+                           rebuilds the coefficients in registers and evaluates the grid from there, Bip never exists in memory
+                           (the fused path); 1 = the coefficient record Bip(nI, 0:pstar) as the reference stores it
+                           (src/ERKIntegrate.f90:555-566), built once at the end of Integrate: the cheaper choice when one
+                           dense output is interpolated many times.  Results are identical. */
 } flint_exec;
 
 /* ---- the partition of an ensemble over shards (devices of one call, or ranks of a multi-process job): trajectory index space
@@ -209,6 +216,10 @@ int flint_erk_interpolate(flint_erk_t*, const double* xarr, long G, double* yarr
  * status[N] (nullable) receives per-trajectory FLINT_ERROR_INTP_ARRAY where xarr leaves [Xint(1),Xint(acc+1)]. */
 int flint_erk_interpolate_batch(flint_erk_t*, const double* xarr, long G, double* yarr, int layout, int* status,
                                 int has_save, int save_coeffs, const flint_exec*);
+/* The same with one grid per trajectory, xarr[N][G] (each row strictly monotone in that trajectory's direction of integration and
+ * inside its span: ERK_class%Interpolate called once per trajectory with its own Xarr, src/ERKInterp.f90:28-76). */
+int flint_erk_interpolate_batch_grids(flint_erk_t*, const double* xarr, long G, double* yarr, int layout, int* status,
+                                      int has_save, int save_coeffs, const flint_exec*);
 
 /* Info (scalar state).  Any pointer may be NULL (= optional absent).  Unlike the reference (quirk Q8)
  * hf/xf/yf are written to the arguments they are named after. */

@@ -252,3 +252,75 @@ def test_params_are_validated():
     K.assert_bit_equal(a["Yf"], b["Yf"], "built-in systems ignore params, as the reference's F")
     c = erk.IntegrateBatch(0.0, y0, 1.0, StepSz=0.0, params=np.arange(9.0))
     assert c["rc"] == F.FLINT_ERROR_PARAMS
+
+
+# ------------------------------------------------------------------------------------------------ dense output, round 2
+@pytest.mark.parametrize("dense_mode", [0, 1])
+@pytest.mark.parametrize("method", METHODS)
+def test_dense_store_grows_instead_of_overflowing(method, dense_mode):
+    """The first level of the dense store is far too small (dense_cap = 128 steps): trajectories are suspended when it is full,
+    get deeper levels and resume -- no step is lost (the reference sizes Xint/Bip for MaxSteps, src/ERKInit.f90:321-332), every
+    trajectory interpolates, final states and counters are untouched.  Both store kinds (step logs + fused Interpolate;
+    coefficient records), both layouts, events on (the event code's steps are logged with their truncated h)."""
+    case = K.cr3bp_case(method, 1e-10, 0, norb=1.0, interp_on=True)
+    N = 300
+    y0 = P.cr3bp_ensemble(N, start=77)
+    G = 401
+    xarr = np.array([case.xf / (G - 1) * i for i in range(G)])
+    xarr[-1] = case.xf
+    o = case.run_oracle(y0, xarr=xarr)
+    assert o["counters"][1].max() > 128                # more than the first level holds (DOP54 / Verner65E: > 2000 steps, four levels)
+    g = case.run_gpu(y0, dense_cap=128, dense_mode=dense_mode)
+    K.compare_batch(g, o, case, "grown store")
+    for layout in (0, 1):
+        st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True, layout=layout)
+        assert st == 0 and (ist == 0).all()
+        K.assert_bit_equal(yarr if layout == 0 else np.transpose(yarr, (2, 1, 0)), o["yarr"], "Yarr layout %d" % layout)
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_config4_shape_fused_and_separate(arith):
+    """Config 4 at its real shape on a 512-orbit sample: Verner98R rtol 1e-11, InterpOn, G = 10 000 uniform points with the last one
+    forced to Xf (tests/test_CR3BP.f90:345-347).  The fused path (step logs -> coefficients in registers -> Yarr) and the separate
+    phases (coefficient records, then the evaluation kernel) both equal the oracle bit for bit; nobody returns INTP_ARRAY."""
+    case = K.cr3bp_case(F.ERK_VERNER98R, 1e-11, arith, interp_on=True, eventset=F.FLINT_EVSET_NONE)
+    N, G = 512, 10000
+    y0 = P.cr3bp_ensemble(N, start=2048)
+    xarr = np.array([case.xf / (G - 1) * i for i in range(G)])
+    xarr[-1] = case.xf
+    o = case.run_oracle(y0, xarr=xarr)
+    for dense_mode in (0, 1):
+        g = case.run_gpu(y0, dense_mode=dense_mode, dense_cap=384)
+        K.compare_batch(g, o, case, "config 4, dense_mode %d" % dense_mode)
+        st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True)
+        assert st == 0 and (ist == 0).all()
+        K.assert_bit_equal(yarr, o["yarr"], "config 4 Yarr, dense_mode %d" % dense_mode)
+        st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, layout=1)
+        K.assert_bit_equal(np.transpose(yarr, (2, 1, 0)), o["yarr"], "config 4 Yarr [nI][G][N], dense_mode %d" % dense_mode)
+
+
+def test_per_trajectory_grids():
+    """flint_erk_interpolate_batch_grids: one grid per trajectory (ragged spans: every trajectory has its own Xf), a backward
+    ensemble, and a row that leaves its trajectory's span (FLINT_ERROR_INTP_ARRAY for that trajectory only)."""
+    for sign in (1.0, -1.0):
+        case = K.twobody_case(F.ERK_DOP853, 1e-10, 0, nper=1, interp_on=True)
+        N, G = 96, 57
+        y0 = P.perturbed_ensemble(P.TBP_Y0, N)
+        xf = sign * np.linspace(0.4, 1.0, N) * P.tbp_period()
+        case.xf = xf
+        grids = np.linspace(0.0, 1.0, G)[None, :] ** 1.5 * xf[:, None]
+        grids[:, -1] = xf
+        for dense_mode in (0, 1):
+            g = case.run_gpu(y0, dense_mode=dense_mode)
+            bad = grids.copy()
+            bad[5] = grids[5] * 1.01
+            st, yarr, ist = g["erk"].InterpolateBatch(bad, N, SaveInterpCoeffs=True)
+            assert ist[5] == F.FLINT_ERROR_INTP_ARRAY and (np.delete(ist, 5) == 0).all()
+            st, yarr, ist = g["erk"].InterpolateBatch(grids, N)
+            assert st == 0 and (ist == 0).all()
+            sc = case.oracle_scalar()
+            for t in (0, 17, N - 1):
+                sc.integrate(0.0, y0[:, t], float(xf[t]), io=case.oracle_int())
+                so, yo = sc.interpolate(grids[t], save=True)
+                assert so == 0
+                K.assert_bit_equal(yarr[t], yo, "per-trajectory grid, trajectory %d" % t)
