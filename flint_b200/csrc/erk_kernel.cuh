@@ -1163,6 +1163,7 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     double* sB = dsm;                                       /* [128][rsp] */
     double* sX = dsm + kDenseBlock * rsp;                   /* [129] (+1 pad) */
     long* sG = reinterpret_cast<long*>(sX + kDenseBlock + 2);   /* [129] */
+    static_assert(kDenseBlock == kEvalSteps, "the block's steps are what the evaluation walks");
     SYS sys;
     sys_load(sys, p);
     if (tid < ns) {
@@ -1222,14 +1223,14 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     const double hs = sign1(sX[1] - sX[0]);                 /* every step points in the direction of integration */
     const double* __restrict__ xg = p.ix + (p.ix_per_traj ? t * p.iG : 0L);
     double* __restrict__ yo = p.iy + t * p.iG * p.nI;
-    const bool first = s0 == 0, last = s0 + ns == ntot;
+    block_step_ranges(sX, sG, ns, s0 == 0, s0 + ns == ntot, xg, p.iG, hs);
     switch (p.nI) {
-    case 1: eval_block_steps<FMA, PS, 1>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
-    case 2: eval_block_steps<FMA, PS, 2>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
-    case 3: eval_block_steps<FMA, PS, 3>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
-    case 4: eval_block_steps<FMA, PS, 4>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
-    case 5: eval_block_steps<FMA, PS, 5>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
-    case 6: if constexpr (N >= 6) eval_block_steps<FMA, PS, 6>(sB, rsp, sX, sG, ns, first, last, xg, p.iG, hs, yo); break;
+    case 1: eval_block_steps<FMA, PS, 1, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
+    case 2: eval_block_steps<FMA, PS, 2, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
+    case 3: eval_block_steps<FMA, PS, 3, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
+    case 4: eval_block_steps<FMA, PS, 4, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
+    case 5: eval_block_steps<FMA, PS, 5, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
+    case 6: if constexpr (N >= 6) eval_block_steps<FMA, PS, 6, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
     default: break;
     }
 }

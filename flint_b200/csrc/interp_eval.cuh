@@ -6,12 +6,9 @@
  *   interp_steps_kernel (interp_kernel.cu): the coefficient records of 128 consecutive steps arrive from HBM as ONE bulk copy
  *       (cp.async.bulk + mbarrier).
  *
- * STEP-MAJOR evaluation: a warp takes one step at a time and puts its lanes on the grid points INSIDE that step, so every
- * coefficient read is a shared-memory broadcast (one wavefront per 16 bytes).  Round 1's kernel put a warp's lanes on 32
- * consecutive points whatever step they fell in: with ~20 points per step (config 4) a batch straddled 2.7 steps and every
- * LDS.128 cost 2.7 wavefronts -- the L1 data pipe, at 78 %, bound the kernel (profiles/r01_notes.md).  The price is lane
- * utilisation (P points occupy ceil(P / 32) batches); the pipe that then binds is fp64, which is where a polynomial
- * evaluation belongs.
+ * The evaluation is point-major within the block's steps (see eval_block_steps).  Strict arithmetic costs ~113 fp64
+ * instructions per 48 bytes written, which puts the fp64 pipe and HBM within 15 % of each other: the phase is co-bound, and what
+ * decides the kernel is how few other instructions and shared-memory wavefronts accompany them.
  *
  * Which step a point belongs to is the reference's forward cursor (:85-103): the smallest j with hs * (Xint(j+1) - x) >= 0,
  * never beyond the last step.  For a grid that is monotone in the direction of integration (validated per trajectory, :60-76)
@@ -29,10 +26,37 @@ namespace flint {
  * of an IEEE difference of finite numbers is exact (gradual underflow), so this is one compare; NaN compares false either way */
 __device__ __forceinline__ bool before_dir(double hs, double X, double x) { return hs > 0.0 ? (X < x) : (X > x); }
 
-/* number of grid points that do not lie beyond X: the first g with before_dir(hs, X, xarr[g]), G if none */
+/* number of grid points that do not lie beyond X: the first g with before_dir(hs, X, xarr[g]), G if none.  The grid is monotone
+ * in the direction hs, so that is a bisection -- started from where X would sit in a uniform grid and widened by doubling, so that
+ * a (nearly) uniform grid costs three or four dependent loads instead of log2(G) */
 __device__ __forceinline__ long grid_count_upto(const double* __restrict__ xarr, long G, double hs, double X)
 {
-    long lo = 0, hi = G;
+    if (G <= 0) return 0;
+    const double xa = xarr[0], xb = xarr[G - 1];
+    long lo = 0, hi = G;                                               /* answer in [lo, hi]; points below lo are not beyond X, point hi is */
+    if (before_dir(hs, X, xa)) return 0;
+    if (!before_dir(hs, X, xb)) return G;
+    {
+        const double fr = (X - xa) / (xb - xa);                        /* in [0, 1] here; a guess only */
+        long c = (long)(fr * (double)(G - 1));
+        c = c < 0 ? 0 : (c > G - 1 ? G - 1 : c);
+        long w = 1;
+        if (before_dir(hs, X, xarr[c])) {                              /* point c lies beyond X: the answer is <= c; walk down */
+            hi = c;
+            for (;;) {
+                const long q = hi - w;
+                if (q <= 0) { lo = 0; break; }
+                if (before_dir(hs, X, xarr[q])) { hi = q; w <<= 1; } else { lo = q + 1; break; }
+            }
+        } else {                                                       /* the answer is > c; walk up */
+            lo = c + 1;
+            for (;;) {
+                const long q = lo + w - 1;
+                if (q >= G - 1) { hi = G - 1; break; }                 /* point G-1 lies beyond X (checked above) */
+                if (before_dir(hs, X, xarr[q])) { hi = q; break; } else { lo = q + 1; w <<= 1; }
+            }
+        }
+    }
     while (lo < hi) {
         const long mid = (lo + hi) >> 1;
         if (before_dir(hs, X, xarr[mid])) hi = mid; else lo = mid + 1;
@@ -40,49 +64,25 @@ __device__ __forceinline__ long grid_count_upto(const double* __restrict__ xarr,
     return lo;
 }
 
-/* InterpY (:124-140) for one point of the step [X0, X1] whose coefficients B[k][ii] sit in shared memory; every lane of the warp
- * reads the same addresses */
-template <bool FMA, int PS, int NI>
-__device__ __forceinline__ void eval_point_bcast(double X0, double X1, double x, const double* __restrict__ B, double (&y)[NI])
-{
-    const double h = X1 - X0;
-    const double theta = (x - X0) / h;
-    double tk[PS + 1];
-    theta_powers<PS>(theta, tk);
-#pragma unroll
-    for (int ii = 0; ii < NI; ++ii) y[ii] = 0.0;
-    if (NI % 2 == 0) {                                 /* two coefficients per 16-byte broadcast */
-        const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
-#pragma unroll
-        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-            for (int q = 0; q < NI / 2; ++q) {
-                const double2 b = B2[k * (NI / 2) + q];
-                y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
-                y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
-            }
-    } else {
-#pragma unroll
-        for (int k = 0; k <= PS; ++k)
-#pragma unroll
-            for (int ii = 0; ii < NI; ++ii) y[ii] = madd<FMA>(B[k * NI + ii], tk[k], y[ii]);
-    }
-}
-
-/* The CTA evaluates the grid points of its `ns` consecutive steps of ONE trajectory.
+/* The CTA evaluates the grid points of its `ns` (<= kEvalSteps) consecutive steps of ONE trajectory.
  *   sB   [ns][rsp]   coefficients of step i at sB + i * rsp (16-byte aligned when NI is even), B[k][ii] k-major
  *   sX   [ns + 1]    sX[i] = start of step i, sX[ns] = end of the last one
  *   sG   [ns + 1]    scratch: sG[i] .. sG[i+1] = the grid points of step i
  *   is_first / is_last: step 0 is the trajectory's first / step ns-1 its last accepted step
- *   yout = Yarr of this trajectory, [G][NI]
- * All threads of the CTA must call it (it synchronises); sB / sX must be visible (a __syncthreads before). */
-template <bool FMA, int PS, int NI>
-__device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, long* __restrict__ sG,
-                                                 int ns, bool is_first, bool is_last, const double* __restrict__ xarr, long G, double hs,
-                                                 double* __restrict__ yout)
+ *   yout = Yarr of this trajectory: [G][NI], or with SOA the trajectory's column of [NI][G][N] (element stride soa_n)
+ * Every warp takes a contiguous share of the steps and walks their points in order, 32 consecutive points per batch (coalesced
+ * loads of x, contiguous stores), but a batch never reaches into a THIRD step: its lanes read the coefficients of at most two
+ * records, so a 16-byte read is at most two shared-memory wavefronts (round 1's kernel let a batch straddle 2.7 steps on
+ * average and was bound by the L1 data pipe at 78 %), and with ~20 points per step the lanes stay ~90 % full.  Measured
+ * alternatives (profiles/r02_notes.md): one step per batch (65 % lanes) and one THREAD per step with its coefficients in
+ * registers, steps ordered by point count (uncoalesced stores: 1.5x slower).
+ * block_step_ranges (all threads, synchronises) fills sG from sX; eval_block_steps then needs sB, sX and sG visible. */
+constexpr int kEvalSteps = 128;
+/* sG[i] .. sG[i+1] = the grid points of step i, for the block's ns steps (all threads; ends with a __syncthreads) */
+__device__ __forceinline__ void block_step_ranges(const double* __restrict__ sX, long* __restrict__ sG, int ns, bool is_first, bool is_last,
+                                                  const double* __restrict__ xarr, long G, double hs)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i <= ns; i += blockDim.x) {
+    for (int i = threadIdx.x; i <= ns; i += blockDim.x) {
         long g;
         if (i == 0) g = is_first ? 0 : grid_count_upto(xarr, G, hs, sX[0]);
         else if (i == ns && is_last) g = G;
@@ -90,25 +90,68 @@ __device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, 
         sG[i] = g;
     }
     __syncthreads();
-    for (int i = warp; i < ns; i += nwarps) {
-        const long g0 = sG[i], g1 = sG[i + 1];
-        const double X0 = sX[i], X1 = sX[i + 1];
-        const double* __restrict__ B = sB + (long)i * rsp;
-        for (long gb = g0; gb < g1; gb += 32) {
-            const long g = gb + lane;
-            if (g < g1) {
-                double y[NI];
-                eval_point_bcast<FMA, PS, NI>(X0, X1, xarr[g], B, y);
-                double* __restrict__ o = yout + g * NI;
+}
+template <bool FMA, int PS, int NI, bool SOA>
+__device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, const long* __restrict__ sG,
+                                                 int ns, const double* __restrict__ xarr, long G, double* __restrict__ yout, long soa_n)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int per = (ns + nwarps - 1) / nwarps;
+    int i = warp * per;
+    const int iend = i + per < ns ? i + per : ns;
+    if (i >= iend) return;
+    long g = sG[i];
+    const long gend = sG[iend];
+    double xn = g + lane < gend ? xarr[g + lane] : 0.0;                /* the next batch's abscissae travel one iteration ahead */
+    while (g < gend) {                                                 /* warp-uniform */
+        while (sG[i + 1] <= g) ++i;                                    /* the step that holds point g (empty steps are skipped) */
+        const long mid = sG[i + 1];                                    /* first point of step i + 1 */
+        const long lim = i + 1 < iend ? sG[i + 2] : mid;               /* a batch ends with step i + 1 at the latest */
+        const long n = lim - g < 32 ? lim - g : 32;
+        const long gl = g + lane;
+        const double x = xn;
+        { const long gq = g + n + lane; xn = gq < gend ? xarr[gq] : 0.0; }
+        if (lane < n) {
+            const int ii = i + (gl >= mid ? 1 : 0);
+            const double X0 = sX[ii], X1 = sX[ii + 1];
+            const double* __restrict__ B = sB + (long)ii * rsp;
+            const double h = X1 - X0;
+            const double theta = (x - X0) / h;                         /* InterpY, :124-140 */
+            double tk[PS + 1], y[NI];
+            theta_powers<PS>(theta, tk);
+#pragma unroll
+            for (int q = 0; q < NI; ++q) y[q] = 0.0;
+            if (NI % 2 == 0) {                                         /* two coefficients per 16-byte read */
+                const double2* __restrict__ B2 = reinterpret_cast<const double2*>(B);
+#pragma unroll
+                for (int k = 0; k <= PS; ++k)
+#pragma unroll
+                    for (int q = 0; q < NI / 2; ++q) {
+                        const double2 b = B2[k * (NI / 2) + q];
+                        y[2 * q] = madd<FMA>(b.x, tk[k], y[2 * q]);
+                        y[2 * q + 1] = madd<FMA>(b.y, tk[k], y[2 * q + 1]);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k <= PS; ++k)
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) y[q] = madd<FMA>(B[k * NI + q], tk[k], y[q]);
+            }
+            if (SOA) {
+#pragma unroll
+                for (int q = 0; q < NI; ++q) yout[((long)q * G + gl) * soa_n] = y[q];
+            } else {
+                double* __restrict__ o = yout + gl * NI;
                 if (NI % 2 == 0) {
 #pragma unroll
                     for (int q = 0; q < NI / 2; ++q) reinterpret_cast<double2*>(o)[q] = make_double2(y[2 * q], y[2 * q + 1]);
                 } else {
 #pragma unroll
-                    for (int ii = 0; ii < NI; ++ii) o[ii] = y[ii];
+                    for (int q = 0; q < NI; ++q) o[q] = y[q];
                 }
             }
         }
+        g += n;
     }
 }
 

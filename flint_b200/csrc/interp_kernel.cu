@@ -117,11 +117,10 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     if (t >= a.N || g0 >= g1) return;
     if (a.status[t] != FLINT_SUCCESS) return;
     const int acc = a.dcount[t];
-    /* single-level store (launch_interp): the trajectory's records are one contiguous run; Xint(j+1) = X1 of record j-1 */
-    const int rstride = a.dv.rstride;
-    const double* __restrict__ rbase = a.dv.base[0] + t * a.dv.cum[1] * (long)rstride;
-    const double* __restrict__ rec0 = rbase + 2;                                       /* coefficients of step 1 */
-    auto xi_at = [&](int j) -> double { return j == 0 ? rbase[0] : rbase[(long)(j - 1) * rstride + 1]; };
+    /* record of step j (1-based) = a.dv.rec(t, j - 1): X0, X1, coefficients; Xint(j+1) = X1 of record j-1.  Nearly every
+     * trajectory lives in level 0 of the store; the few that grew deeper levels pay a short loop per record */
+    auto recp = [&](int j) -> const double* { return a.dv.rec(t, (long)j - 1); };
+    auto xi_at = [&](int j) -> double { return j == 0 ? recp(1)[0] : recp(j)[1]; };
     const double hs = sign1(xi_at(acc) - xi_at(0));
     /* chunk start: smallest j in [1,acc] (1-based) with hs*(Xint(j+1) - x) >= 0 */
     int loc;
@@ -137,10 +136,10 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
     }
     double B[PS + 1][NI];
     double X0 = xi_at(loc - 1), X1, h;
-    RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * rstride, rbase + (long)(loc - 1) * rstride + 1);
+    { const double* r = recp(loc); RecBuf<RS>::prefetch(rb, r + 2, r + 1); }
     RecBuf<RS>::take(rb, &B[0][0], X1);                               /* step loc: coefficients and Xint(loc+1) */
     h = X1 - X0;
-    if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * rstride, rbase + (long)loc * rstride + 1);
+    if (loc < acc) { const double* r = recp(loc + 1); RecBuf<RS>::prefetch(rb, r + 2, r + 1); }
     for (long g = g0; g < g1; ++g) {
         const double x = xs[g - g0];
         if (loc < acc && before(hs, X1, x)) {                         /* forward cursor (:85-103) */
@@ -149,11 +148,11 @@ __global__ void __launch_bounds__(128) interp_kernel_soa(InterpArgs a)
             RecBuf<RS>::take(rb, &B[0][0], X1);                       /* the record that was on its way */
             if (loc < acc && before(hs, X1, x)) {                     /* several steps between two grid points: walk Xint */
                 do { loc += 1; X0 = X1; X1 = xi_at(loc); } while (loc < acc && before(hs, X1, x));
-                RecBuf<RS>::prefetch(rb, rec0 + (long)(loc - 1) * rstride, rbase + (long)(loc - 1) * rstride + 1);
+                { const double* r = recp(loc); RecBuf<RS>::prefetch(rb, r + 2, r + 1); }
                 RecBuf<RS>::take(rb, &B[0][0], X1);
             }
             h = X1 - X0;
-            if (loc < acc) RecBuf<RS>::prefetch(rb, rec0 + (long)loc * rstride, rbase + (long)loc * rstride + 1);
+            if (loc < acc) { const double* r = recp(loc + 1); RecBuf<RS>::prefetch(rb, r + 2, r + 1); }
         }
         const double theta = (x - X0) / h;
         double tk[PS + 1];
@@ -200,13 +199,20 @@ static cudaError_t launch_soa_one(const InterpArgs& a, dim3 grid, cudaStream_t s
  * the TMA engine's 1-D form) into shared memory; the CTA then evaluates step-major with broadcast reads (interp_eval.cuh).
  * Three CTAs are resident per SM (3 x 58 KB), so one block's copy travels while the others compute.
  * ====================================================================================================== */
-constexpr int kStepsBlock = 128;       /* steps per CTA */
-constexpr int kStepsThreads = 256;
+#ifndef FLINT_STEPS_TILE
+#define FLINT_STEPS_TILE 64
+#endif
+#ifndef FLINT_STEPS_THREADS
+#define FLINT_STEPS_THREADS 128
+#endif
+constexpr int kStepsBlock = FLINT_STEPS_TILE;      /* steps per CTA (divides the 128-step granularity of the capacity levels) */
+constexpr int kStepsThreads = FLINT_STEPS_THREADS;
+constexpr int kStepsResident = 65536 / (80 * kStepsThreads) < 16 ? 65536 / (80 * kStepsThreads) : 16;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <bool FMA, int PS, int NI, bool SOA>
-__global__ void __launch_bounds__(kStepsThreads, 3) interp_steps_kernel(InterpArgs a)
+__global__ void __launch_bounds__(kStepsThreads, kStepsResident) interp_steps_kernel(InterpArgs a)
 {
     const long t = blockIdx.x;
     if (a.status[t] != FLINT_SUCCESS) return;                          /* validated before (launch_interp) */
@@ -229,7 +235,13 @@ __global__ void __launch_bounds__(kStepsThreads, 3) interp_steps_kernel(InterpAr
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sR)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
     }
-    __syncthreads();                                                   /* the barrier is initialised before anyone polls it */
+    /* while the records travel: the step boundaries straight from HBM (8 bytes per step) and, from them, every step's range of
+     * grid points -- the bisection's dependent loads overlap the bulk copy instead of following it */
+    for (int i = threadIdx.x; i <= ns; i += blockDim.x) sX[i] = i < ns ? src[(long)i * rstride] : src[(long)(ns - 1) * rstride + 1];
+    __syncthreads();                                                   /* also: the barrier is initialised before anyone polls it */
+    const double hs = sign1(sX[1] - sX[0]);
+    const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+    block_step_ranges(sX, sG, ns, s0 == 0, s0 + ns == acc, xg, a.G, hs);
     {
         unsigned ok = 0;
         do {
@@ -237,37 +249,8 @@ __global__ void __launch_bounds__(kStepsThreads, 3) interp_steps_kernel(InterpAr
                          : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
         } while (!ok);
     }
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        sX[i] = sR[(long)i * rstride];
-        if (i == ns - 1) sX[ns] = sR[(long)i * rstride + 1];
-    }
-    __syncthreads();
-    const double hs = sign1(sX[1] - sX[0]);
-    const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
-    if (!SOA) {
-        eval_block_steps<FMA, PS, NI>(sR + 2, rstride, sX, sG, ns, s0 == 0, s0 + ns == acc, xg, a.G, hs, a.yarr + t * a.G * NI);
-    } else {
-        /* [nI][G][N]: the same evaluation with one 8-byte store per state (small ensembles, grown stores) */
-        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-        for (int i = tid; i <= ns; i += blockDim.x) {
-            long g;
-            if (i == 0) g = s0 == 0 ? 0 : grid_count_upto(xg, a.G, hs, sX[0]);
-            else if (i == ns && s0 + ns == acc) g = a.G;
-            else g = grid_count_upto(xg, a.G, hs, sX[i]);
-            sG[i] = g;
-        }
-        __syncthreads();
-        for (int i = warp; i < ns; i += nwarps)
-            for (long gb = sG[i]; gb < sG[i + 1]; gb += 32) {
-                const long g = gb + lane;
-                if (g < sG[i + 1]) {
-                    double y[NI];
-                    eval_point_bcast<FMA, PS, NI>(sX[i], sX[i + 1], xg[g], sR + (long)i * rstride + 2, y);
-#pragma unroll
-                    for (int ii = 0; ii < NI; ++ii) a.yarr[((long)ii * a.G + g) * a.N + t] = y[ii];
-                }
-            }
-    }
+    double* yo = SOA ? a.yarr + t : a.yarr + t * a.G * NI;            /* [nI][G][N]: this trajectory's column */
+    eval_block_steps<FMA, PS, NI, SOA>(sR + 2, rstride, sX, sG, ns, xg, a.G, yo, a.N);
 }
 
 template <bool FMA, int PS, int NI>
@@ -348,8 +331,8 @@ cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, 
     InterpArgs a = a0;
     const cudaError_t ev = launch_interp_validate(a, up, down, s);
     if (ev != cudaSuccess) return ev;
-    /* structure-of-arrays output, enough trajectories to fill the device with threads, one shared grid, records in one run */
-    if (a.layout != 0 && a.N >= 4096 && a.dv.nlev == 1 && !a.per_traj) {
+    /* structure-of-arrays output, enough trajectories to fill the device with threads, one shared grid */
+    if (a.layout != 0 && a.N >= 4096 && !a.per_traj) {
         const long want_t = (long)sm_count * 16 * 32;
         long nc = (want_t + a.N - 1) / a.N;
         const long min_nc = (a.G + FLINT_INTERP_CHUNK - 1) / FLINT_INTERP_CHUNK;

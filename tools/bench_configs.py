@@ -43,51 +43,83 @@ if "lorenz" in which:      # config 2: Lorenz, 2^20 perturbed ICs, DOP54, rtol 1
              attempts_per_traj=float(cnt[0].mean()), tflops_alg=fl / ms / 1e9, frac_fp64_peak=fl / ms / 1e9 / peak_tf,
              ok=float((r["status"] == 0).float().mean()))
 
-if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolation onto a shared uniform grid
-    # BASELINE's 2^18 orbits: Yarr alone is 125.8 GB, so one GPU runs them as two shards of 2^17 back to back
-    # (Yarr 62.9 GB + dense store 37 GB each); the times below are the sums over both shards.
+if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolation onto a shared uniform grid (SURVEY.md 8d)
+    # Reported three ways: the phases SEPARATELY (Integrate builds coefficient records, dense_mode 1; Interpolate evaluates them,
+    # both layouts), FUSED (Integrate keeps step logs; Interpolate rebuilds the coefficients in registers and evaluates from
+    # there, Bip never in memory), and the fused path on all 2^18 orbits as ONE pair of calls (Yarr 125.8 GB + 29.5 GB of logs).
+    # The separate phases need Yarr + 37 GB of records per 2^17 orbits, so they run as two shards back to back.
+    import gc
     SH = 1 << (14 if small else 17)
     NSH = 2
     G = 10000
+    CAP = 640
+
+    def timed_interp(erk, xarr, n, layout, yarr):
+        best, ist = 1e30, None
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st, _, ist = erk.InterpolateBatch(xarr, n, SaveInterpCoeffs=True, layout=layout, out=yarr)
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best, ist
+
     for arith in (0, 1):
-        t_int, t_itp, fl_tot, acc_tot, n_ok, n_int_ok = 0.0, [0.0, 0.0], 0.0, 0, 0, 0
-        for sh in range(NSH):
-            sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
-            y0 = torch.from_numpy(P.cr3bp_ensemble(SH, start=sh * SH)).cuda()
-            ms, r = run(erk, 0.0, y0, xf, reps=2, dense_cap=640, **ikw)      # best of 2: the first call of a process also loads the kernels
-            cnt = r["counters"].cpu().numpy().astype(np.int64)
-            fl_tot += P.algorithmic_flops(F.ERK_VERNER98R, F.FLINT_SYS_CR3BP_PLANAR, 6, cnt[0].sum(), cnt[1].sum(), cnt[1].sum())
-            acc_tot += int(cnt[1].sum())
-            t_int += ms
-            n_int_ok += int((r["status"] == 0).sum())
+        for mode, mname in ((1, "separate"), (0, "fused")):
+            t_int, t_itp, fl_tot, acc_tot, n_ok, n_int_ok = 0.0, [0.0, 0.0], 0.0, 0, 0, 0
+            for sh in range(NSH):
+                sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
+                y0 = torch.from_numpy(P.cr3bp_ensemble(SH, start=sh * SH)).cuda()
+                ms, r = run(erk, 0.0, y0, xf, reps=2, dense_cap=CAP, dense_mode=mode, **ikw)      # best of 2: the first call of a process also loads the kernels
+                cnt = r["counters"].cpu().numpy().astype(np.int64)
+                fl_tot += P.algorithmic_flops(F.ERK_VERNER98R, F.FLINT_SYS_CR3BP_PLANAR, 6, cnt[0].sum(), cnt[1].sum(), cnt[1].sum())
+                acc_tot += int(cnt[1].sum())
+                t_int += ms
+                n_int_ok += int((r["status"] == 0).sum())
+                xarr = torch.linspace(0.0, xf, G, dtype=torch.float64).cuda()
+                xarr[-1] = xf
+                for layout in ((0, 1) if mode == 1 else (0,)):
+                    yarr = torch.empty((SH, G, 6) if layout == 0 else (6, G, SH), dtype=torch.float64, device="cuda")
+                    best, ist = timed_interp(erk, xarr, SH, layout, yarr)
+                    t_itp[layout] += best
+                    if layout == 0:
+                        n_ok += int((ist == 0).sum())
+                    del yarr
+                del erk, y0, xarr
+                gc.collect(); torch.cuda.empty_cache()
+            N = SH * NSH
+            gb_w = N * G * 6 * 8 / 1e9
+            gb_r = acc_tot * (54 + 2) * 8 / 1e9          # separate: every coefficient record (X0, X1, 9 x 6 coefficients) read once
+            gb_log = acc_tot * 14 * 8 / 1e9              # fused: every step log (X, h, Y, F0) read once
+            emit(config=4, mode=mname, what="Integrate phase (%s)" % ("steps + coefficient records" if mode == 1 else "steps, logs only"), arith=arith,
+                 N=N, shards=NSH, ms=t_int, value=N / t_int * 1e3, unit="orbits/s", accepted_per_orbit=acc_tot / N, tflops_alg=fl_tot / t_int / 1e9,
+                 frac_fp64_peak=fl_tot / t_int / 1e9 / peak_tf, integrated_fraction=n_int_ok / N)
+            for layout in ((0, 1) if mode == 1 else (0,)):
+                rd = gb_r if mode == 1 else gb_log
+                emit(config=4, mode=mname, what="Interpolate onto %d-point grid, layout %d%s" % (G, layout, "" if mode == 1 else " (coefficients rebuilt in registers)"),
+                     arith=arith, N=N, shards=NSH, ms=t_itp[layout], yarr_gb=gb_w, read_gb=rd, gbs_written=gb_w / t_itp[layout] * 1e3,
+                     gbs_total=(gb_w + rd) / t_itp[layout] * 1e3, frac_hbm_peak_written=gb_w / t_itp[layout] * 1e3 / HBM_GBS,
+                     frac_hbm_peak=(gb_w + rd) / t_itp[layout] * 1e3 / HBM_GBS, points_per_s=N * G / t_itp[layout] * 1e3,
+                     interpolated_fraction=n_ok / N)
+            emit(config=4, mode=mname, what="Integrate + Interpolate [N][G][nI], total", arith=arith, N=N, ms=t_int + t_itp[0],
+                 orbits_per_s=N / (t_int + t_itp[0]) * 1e3)
+    if not small:          # the whole of config 4 as one Integrate and one Interpolate call on one GPU (fused path only: it fits)
+        try:
+            N = 1 << 18
+            sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=0, interp_on=True)
+            y0 = torch.from_numpy(P.cr3bp_ensemble(N)).cuda()
+            ms, r = run(erk, 0.0, y0, xf, reps=1, dense_cap=CAP, dense_mode=0, **ikw)
             xarr = torch.linspace(0.0, xf, G, dtype=torch.float64).cuda()
             xarr[-1] = xf
-            for layout in (0, 1):
-                yarr = torch.empty((SH, G, 6) if layout == 0 else (6, G, SH), dtype=torch.float64, device="cuda")
-                best = 1e30
-                for _ in range(2):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    st, _, ist = erk.InterpolateBatch(xarr, SH, SaveInterpCoeffs=True, layout=layout, out=yarr)
-                    e1.record(); torch.cuda.synchronize()
-                    best = min(best, e0.elapsed_time(e1))
-                t_itp[layout] += best
-                if layout == 0:
-                    n_ok += int((ist == 0).sum())
-                del yarr
-            del erk, y0, xarr
-            import gc; gc.collect(); torch.cuda.empty_cache()
-        N = SH * NSH
-        emit(config=4, what="CR3BP Verner98R + dense coefficients, orbits/s (integrate phase)", arith=arith, N=N, shards=NSH, ms=t_int,
-             value=N / t_int * 1e3, unit="orbits/s", accepted_per_orbit=acc_tot / N, tflops_alg=fl_tot / t_int / 1e9,
-             frac_fp64_peak=fl_tot / t_int / 1e9 / peak_tf, dense_store_gb=acc_tot * 440 / 1e9)
-        gb_w = N * G * 6 * 8 / 1e9
-        gb_r = acc_tot * (54 + 1) * 8 / 1e9              # every step record (9 x 6 coefficients + its end abscissa) read once
-        for layout in (0, 1):
-            emit(config=4, what="Interpolate onto %d-point grid, layout %d" % (G, layout), arith=arith, N=N, shards=NSH, ms=t_itp[layout],
-                 yarr_gb=gb_w, records_gb=gb_r, gbs_written=gb_w / t_itp[layout] * 1e3, gbs_total=(gb_w + gb_r) / t_itp[layout] * 1e3,
-                 frac_hbm_peak_written=gb_w / t_itp[layout] * 1e3 / HBM_GBS, frac_hbm_peak=(gb_w + gb_r) / t_itp[layout] * 1e3 / HBM_GBS,
-                 points_per_s=N * G / t_itp[layout] * 1e3, interpolated_fraction=n_ok / N, integrated_fraction=n_int_ok / N)
+            yarr = torch.empty((N, G, 6), dtype=torch.float64, device="cuda")
+            best, ist = timed_interp(erk, xarr, N, 0, yarr)
+            emit(config=4, mode="fused, one call", what="2^18 orbits: one Integrate + one Interpolate call", arith=0, N=N, integrate_ms=ms, interpolate_ms=best,
+                 interpolated_fraction=float((ist == 0).float().mean()), yarr_gb=N * G * 48 / 1e9,
+                 device_mem_gb=torch.cuda.mem_get_info()[1] / 1e9, orbits_per_s=N / (ms + best) * 1e3)
+            del yarr, y0, erk
+            gc.collect(); torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            emit(config=4, mode="fused, one call", error=str(e)[:300])
 
 if "wp" in which:          # config 5: work-precision sweep, spatial CR3BP halo and two-body, all four methods
     N = 1 << (12 if small else 16)
