@@ -78,12 +78,19 @@ module FLINT_GPU
         integer(c_long) :: cap = 0
         type(c_ptr) :: rec = c_null_ptr, count = c_null_ptr
     end type
+    integer, parameter, public :: FLINT_MAX_DEVICES = 16
+    !> include/flint_b200.h: flint_exec, field for field (where the buffers live, which GPUs run the call, tuning knobs)
     type, bind(C), public :: flint_exec
         integer(c_int) :: mem = 0, device = 0
         type(c_ptr) :: stream = c_null_ptr
         integer(c_int) :: async = 0
         integer(c_long) :: dense_cap = 0
         integer(c_int) :: block_threads = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0
+        integer(c_int) :: round_len = 0
+        integer(c_int) :: n_devices = 0                       ! > 1: the ensemble is sharded over devices(1:n_devices) inside the call
+        integer(c_int) :: devices(FLINT_MAX_DEVICES) = 0
+        integer(c_long) :: shard_chunk = 0
+        integer(c_int) :: dense_mode = 0
     end type
 
     interface
@@ -121,6 +128,22 @@ module FLINT_GPU
             import; type(c_ptr), value :: h; integer(c_long), value :: g; integer(c_int), value :: has_save, save_coeffs
             real(c_double), intent(in) :: xarr(*); real(c_double), intent(out) :: yarr(*); integer(c_int) :: st
         end function
+        function flint_erk_interpolate_batch(h, xarr, g, yarr, layout, status, has_save, save_coeffs, exec) &
+                bind(C, name="flint_erk_interpolate_batch") result(st)
+            import; type(c_ptr), value :: h, xarr, yarr, status; integer(c_long), value :: g
+            integer(c_int), value :: layout, has_save, save_coeffs; type(flint_exec), intent(in) :: exec; integer(c_int) :: st
+        end function
+        function flint_erk_interpolate_batch_grids(h, xarr, g, yarr, layout, status, has_save, save_coeffs, exec) &
+                bind(C, name="flint_erk_interpolate_batch_grids") result(st)
+            import; type(c_ptr), value :: h, xarr, yarr, status; integer(c_long), value :: g
+            integer(c_int), value :: layout, has_save, save_coeffs; type(flint_exec), intent(in) :: exec; integer(c_int) :: st
+        end function
+        function flint_b200_device_count() bind(C, name="flint_b200_device_count") result(n)
+            import; integer(c_int) :: n
+        end function
+        function flint_b200_shard_count(n, n_shards, shard, chunk) bind(C, name="flint_b200_shard_count") result(c)
+            import; integer(c_long), value :: n, chunk; integer(c_int), value :: n_shards, shard; integer(c_long) :: c
+        end function
         function flint_erk_info(h, last_status, nsteps, naccept, nreject, nfcalls, interp_ready, x0, y0, hf, xf, yf) &
                 bind(C, name="flint_erk_info") result(st)
             import; type(c_ptr), value :: h, last_status, nsteps, naccept, nreject, nfcalls, interp_ready, x0, y0, hf, xf, yf
@@ -130,6 +153,8 @@ module FLINT_GPU
             import; integer(c_int), value :: s; type(c_ptr) :: p
         end function
     end interface
+
+    public :: flint_b200_device_count, flint_b200_shard_count
 
     !> DiffEqSys of the GPU build: F and G are device functors compiled into the library.
     type, public :: DiffEqSys_GPU
@@ -150,6 +175,7 @@ module FLINT_GPU
         procedure :: Integrate => erk_int
         procedure :: IntegrateBatch => erk_int_batch
         procedure :: Interpolate => erk_interp
+        procedure :: InterpolateBatch => erk_interp_batch
         procedure :: Info => erk_info
         final :: erk_final
     end type
@@ -265,7 +291,11 @@ contains
         if (present(EventStates)) EventStates = EventStates(:, 1:min(nev, MaxEvents))
     end subroutine
 
-    !> Ensemble form: Y0(N, n) in Fortran = SoA [n][N] in C.  Outputs likewise.
+    !> Ensemble form: Y0(N, n) in Fortran = SoA [n][N] in C.  Outputs likewise.  exec%n_devices > 1 shards the ensemble over
+    !! the GPUs of the box inside this one call (block-cyclic chunks of 4096 trajectories, SURVEY.md 8e): the loop over
+    !! trajectories of tests/test_CR3BP.f90:397-405 becomes
+    !!     ex%n_devices = flint_b200_device_count();  ex%devices(1:ex%n_devices) = [(i - 1, i = 1, ex%n_devices)]
+    !!     call erk%IntegrateBatch(x0, Y0, Xf, Yf, StepSz, Counters, Status, EventMask=EvMask, EventCount=nEv, EventStates=Ev, exec=ex)
     subroutine erk_int_batch(me, X0, Y0, Xf, Yf, StepSz, Counters, Status, UseConstStepSz, EventMask, EventCount, &
                              EventStates, StiffTest, exec)
         class(ERK_class), intent(inout) :: me
@@ -306,6 +336,36 @@ contains
         hs = 0; sv = 0
         if (present(SaveInterpCoeffs)) then; hs = 1; sv = merge(1, 0, SaveInterpCoeffs); end if
         me%status = flint_erk_interpolate(me%handle, Xarr, size(Xarr, kind=c_long), Yarr, hs, sv)
+    end subroutine
+
+    !> Interpolate for the ensemble of the last IntegrateBatch (src/ERKInterp.f90:28-140 once per trajectory).
+    !! Xarr(G): one grid for all trajectories, Yarr(nI, G, N): trajectory i's Yarr(nI, G) is Yarr(:, :, i), exactly the array the
+    !! reference's Interpolate fills (C layout 0, [N][G][nI]).  XarrPerTraj(G, N): one grid per trajectory instead.
+    !! Status(N): FLINT_ERROR_INTP_ARRAY where a grid leaves its trajectory's span (:60-76).
+    subroutine erk_interp_batch(me, Yarr, Xarr, XarrPerTraj, Status, SaveInterpCoeffs, exec)
+        class(ERK_class), intent(inout) :: me
+        real(WP), dimension(:,:,:), intent(out), target :: Yarr                       ! (nI, G, N)
+        real(WP), dimension(:), intent(in), optional, target :: Xarr                   ! (G)
+        real(WP), dimension(:,:), intent(in), optional, target :: XarrPerTraj          ! (G, N)
+        integer(c_int), dimension(:), intent(out), optional, target :: Status          ! (N)
+        logical, intent(in), optional :: SaveInterpCoeffs
+        type(flint_exec), intent(in), optional :: exec
+        type(flint_exec) :: ex
+        type(c_ptr) :: pst
+        integer(c_int) :: hs, sv
+        hs = 0; sv = 0
+        if (present(SaveInterpCoeffs)) then; hs = 1; sv = merge(1, 0, SaveInterpCoeffs); end if
+        if (present(exec)) ex = exec
+        pst = c_null_ptr
+        if (present(Status)) pst = c_loc(Status)
+        if (present(XarrPerTraj)) then
+            me%status = flint_erk_interpolate_batch_grids(me%handle, c_loc(XarrPerTraj), size(XarrPerTraj, 1, kind=c_long), c_loc(Yarr), &
+                                                          0_c_int, pst, hs, sv, ex)
+        else if (present(Xarr)) then
+            me%status = flint_erk_interpolate_batch(me%handle, c_loc(Xarr), size(Xarr, kind=c_long), c_loc(Yarr), 0_c_int, pst, hs, sv, ex)
+        else
+            me%status = FLINT_ERROR_PARAMS
+        end if
     end subroutine
 
     !> src/FLINT_base.f90:507-533 (hf/Xf/Yf are returned in the arguments they are named after; quirk Q8 fixed)

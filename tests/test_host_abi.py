@@ -202,3 +202,51 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def _c_struct_fields(name):
+    """Field names of `typedef struct { ... } name;` in include/flint_b200.h, in order."""
+    txt = open(os.path.join(ROOT, "include", "flint_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    body = re.search(r"typedef struct \{([^{}]*)\} %s;" % name, txt).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            m = re.search(r"(\w+)\s*(\[[^\]]*\])?\s*$", part.strip())
+            names.append(m.group(1))
+    return names
+
+
+def _fortran_type_fields(name):
+    txt = open(os.path.join(ROOT, "fortran", "flint_gpu.f90")).read()
+    body = re.search(r"type, bind\(C\)(?:, public)? :: %s\n(.*?)end type" % name, txt, flags=re.S).group(1)
+    names = []
+    for line in body.splitlines():
+        line = line.split("!")[0]
+        if "::" not in line:
+            continue
+        for part in re.split(r",(?![^()]*\))", line.split("::")[1]):
+            names.append(re.match(r"\s*(\w+)", part).group(1))
+    return names
+
+
+def test_abi_structs_agree_between_c_header_ctypes_and_fortran():
+    """The three descriptions of the ABI structs (include/flint_b200.h, flint_b200/api.py, fortran/flint_gpu.f90) list the same
+    fields in the same order -- the Fortran module cannot be compiled in this image, so at least its layout is pinned."""
+    strip = lambda names: [n.rstrip("_") for n in names]  # noqa: E731
+    for cname, ctype in (("flint_exec", api._Exec), ("flint_init_opts", api._InitOpts), ("flint_int_opts", api._IntOpts),
+                         ("flint_steps_out", api._StepsOut), ("flint_events_out", api._EventsOut)):
+        c = _c_struct_fields(cname)
+        assert strip([f[0] for f in ctype._fields_]) == c, cname
+        assert _fortran_type_fields(cname) == c, cname
+    # size check of the largest one against the C compiler's own layout
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include "flint_b200.h"\nint main(void){printf("%zu %zu %zu", sizeof(flint_exec), sizeof(flint_init_opts), sizeof(flint_int_opts));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "s.c"), "-o", os.path.join(td, "s")], check=True)
+        sizes = [int(v) for v in subprocess.run([os.path.join(td, "s")], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(api._Exec), C.sizeof(api._InitOpts), C.sizeof(api._IntOpts)]
