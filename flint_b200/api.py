@@ -112,6 +112,7 @@ def lib():
         L.flint_sys_create.restype = C.c_void_p
         L.flint_sys_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.flint_sys_destroy.argtypes = [C.c_void_p]
+        L.flint_sys_register_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         L.flint_erk_create.restype = C.c_void_p
         L.flint_erk_destroy.argtypes = [C.c_void_p]
         L.flint_erk_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_InitOpts)]
@@ -168,6 +169,24 @@ def _ptr(x):
         return x.data_ptr()
     assert x.flags["C_CONTIGUOUS"]
     return x.ctypes.data
+
+
+def register_system_source(struct_name, source, has_events=False):
+    """Run-time registration of a user DiffEqSys (include/flint_b200.h: flint_sys_register_source): `source` is the text of a
+    header defining `struct <struct_name> : flint::UserSystem<n, m_max>` (F = accel<FMA>, G = events); NVRTC compiles it against
+    the library's kernel headers.  Returns the system id for DiffEqSys(id, ...).  Raises ValueError with the compiler's log."""
+    out = C.c_int(0)
+    rc = lib().flint_sys_register_source(struct_name.encode(), source.encode(), int(bool(has_events)), C.byref(out))
+    if rc != FLINT_SUCCESS:
+        raise ValueError("flint_sys_register_source (%s): %s" % (status_string(rc), last_error()))
+    return out.value
+
+
+def precompile_system(system_id, Method=ERK_DOP853, Arith=FLINT_ARITH_STRICT, EventsOn=False):
+    """Compile and cache the integrate kernels of a system registered from source, without a GPU (flint_sys_precompile)."""
+    rc = lib().flint_sys_precompile(int(system_id), int(Method), int(Arith), int(bool(EventsOn)))
+    if rc != FLINT_SUCCESS:
+        raise ValueError("flint_sys_precompile (%s): %s" % (status_string(rc), last_error()))
 
 
 class DiffEqSys:

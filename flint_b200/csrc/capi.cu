@@ -28,6 +28,19 @@ static std::atomic<long> g_launches{0};                 /* handles on different 
 static std::atomic<double> g_last_kernel_ms{0.0};
 
 static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+namespace flint {
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+/* rtc.cu: systems registered from source at run time */
+const KernelEntry* build_rt_kernel(int method, int system, bool fma, bool events);
+bool rt_system_facts(int system, int* n, int* m_max, int* has_events);
+/* the kernels of a combination: compiled into the library, already built at run time, or built now */
+static const KernelEntry* get_kernel(int method, int system, bool fma, bool events)
+{
+    const KernelEntry* ke = find_kernel(method, system, fma, events);
+    if (!ke && system >= FLINT_SYS_USER_BASE) ke = build_rt_kernel(method, system, fma, events);
+    return ke;
+}
+}  // namespace flint
 static bool cuda_ok(cudaError_t e, const char* what)
 {
     if (e == cudaSuccess) return true;
@@ -168,11 +181,15 @@ extern "C" flint_sys_t* flint_sys_create(int system_id, int eventset_id, int n, 
     case FLINT_SYS_LORENZ: need_n = 3; max_m = 0; break;
     case FLINT_SYS_TWOBODY: need_n = 6; max_m = 1; break;
     default:
-        if (system_id >= FLINT_SYS_USER_BASE) {            /* registered at build time (csrc/systems.cuh) */
-            const flint::KernelEntry* ke = flint::find_system(system_id);
-            if (!ke) { g_last_error = "flint_sys_create: no user system with this id is compiled into the library"; return nullptr; }
-            if (n != ke->sys_n || m < 0 || m > ke->sys_m_max || m > FLINT_MAX_M || (eventset_id == FLINT_EVSET_NONE && m != 0) ||
-                eventset_id < 0 || nsysparams < 0 || nsysparams > 7) {
+        if (system_id >= FLINT_SYS_USER_BASE) {            /* registered at build time (csrc/systems.cuh) or at run time (rtc.cu) */
+            int sys_n = 0, sys_m_max = 0, has_ev = 1;
+            if (const flint::KernelEntry* ke = flint::find_system(system_id)) { sys_n = ke->sys_n; sys_m_max = ke->sys_m_max; }
+            else if (!flint::rt_system_facts(system_id, &sys_n, &sys_m_max, &has_ev)) {
+                g_last_error = "flint_sys_create: no user system with this id is compiled into the library or registered (flint_sys_register_source)";
+                return nullptr;
+            }
+            if (n != sys_n || m < 0 || m > sys_m_max || m > FLINT_MAX_M || (eventset_id == FLINT_EVSET_NONE && m != 0) ||
+                (m > 0 && !has_ev) || eventset_id < 0 || nsysparams < 0 || nsysparams > 7) {
                 g_last_error = "flint_sys_create: n/m/eventset do not match the registered user functor";
                 return nullptr;
             }
@@ -483,7 +500,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
 
     if (!cuda_ok(cudaSetDevice(ex.device), "cudaSetDevice")) return me->status = FLINT_ERROR;
     const bool dense = me->interp_on;
-    const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, events_on);
+    const flint::KernelEntry* ke = flint::get_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, events_on);
+    if (!ke && !g_last_error.empty()) return me->status = FLINT_ERROR;    /* a run-time system whose kernels failed to build: the compiler's log */
     if (!ke) {
         char buf[160];
         snprintf(buf, sizeof buf, "no kernel compiled for method=%d system=%d arith=%d events=%d dense=%d", me->method,
@@ -504,23 +522,23 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
     a.round_req = ex.round_len;
     if (io->present & FLINT_INT_PARAMS) { a.n_params = io->n_params; for (int i = 0; i < io->n_params; ++i) a.params[i] = io->params[i]; }
 
-    ke->load_coefficients(a.coef);
+    flint::load_method_coefficients(me->method, a.coef);
     flint::det_pow_constants(a.powc);
 
     /* events that are located on (nearly) every step keep the in-loop handling; otherwise park + batch */
-    bool park = events_on && ke->step_park && ke->event;
+    bool park = events_on && ke->step_park.classic && ke->event;
     if (park)
         for (int i = 0; i < m; ++i)
             if (((evmask >> i) & 1u) && me->ev_stepsz[i] != 0.0) park = false;
     if (ex.event_mode == 1) park = false;
-    if (ex.event_mode == 2 && events_on && ke->step_park) park = true;
+    if (ex.event_mode == 2 && events_on && ke->step_park.classic) park = true;
 
     /* persistent lanes: the step kernels size themselves (one resident wave of their own CTA size, erk_kernel.cuh: StepCfg) */
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ex.device);
     /* plane variant: trajectories with identically zero components (csrc/systems.cuh: SysCR3BPPlanarZ).  The dropped
      * components contribute (0/Sc)^2 to the error norms, so Sc = ATol must be positive there. */
-    bool try_plane = ke->step_plane != nullptr && (!events_on || park) && ex.plane_variant != 2;
+    bool try_plane = ke->step_plane.classic != nullptr && (!events_on || park) && ex.plane_variant != 2;
     if (try_plane) {
         unsigned zp = sys.system_id == FLINT_SYS_CR3BP_PLANAR ? ((1u << 2) | (1u << 5)) : 0u;
         for (int c = 0; c < n; ++c)
@@ -682,8 +700,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             c.n_items_exact = 1;                               /* the host knows how many trajectories this pass runs (gang-scheduled kernel) */
             if (!park) {
                 c.list_in = in; c.n_in = n_in; c.list_out = nullptr; c.n_out = nullptr;
-                if (try_plane) { le = ke->step_plane(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* returns at once unless the flag is set */
-                if (le == cudaSuccess) { le = ke->step(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                if (try_plane) { le = flint::launch_step(ke->step_plane, c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }   /* returns at once unless the flag is set */
+                if (le == cudaSuccess) { le = flint::launch_step(ke->step, c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
                 return le;
             }
             /* pass 0; then rounds of {locate the parked events, resume}.  Synchronous calls read the parked count and stop when
@@ -692,8 +710,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             const int max_rounds = fixed_schedule ? 3 : 64;
             int cur = 1;                                               /* index of the counter of the list being filled */
             c.list_in = in; c.n_in = n_in; c.list_out = listA; c.n_out = ctr + 1;
-            if (try_plane) { le = ke->step_plane(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
-            if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+            if (try_plane) { le = flint::launch_step(ke->step_plane, c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = flint::launch_step(ke->step_park, c, dev_sms, n_items, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
             for (int round = 0; round < max_rounds && le == cudaSuccess; ++round) {
                 long n_parked = n_items;
                 if (!fixed_schedule) {
@@ -709,7 +727,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 const int oth = cur == 1 ? 2 : 1;
                 c.list_in = lcur; c.n_in = ctr + cur; c.list_out = loth; c.n_out = ctr + oth;
                 c.n_items_exact = fixed_schedule ? 0 : 1;      /* synchronous calls know every pass's item count */
-                le = ke->event(c, (int)((n_parked + 127) / 128), 128, s);   /* also re-arms work_counter and zeroes |other| */
+                le = flint::launch_kernel(ke->event, c, dim3((unsigned)((n_parked + 127) / 128)), 128, 0, s);   /* also re-arms work_counter and zeroes |other| */
                 g_launches += 1;
                 if (le != cudaSuccess) break;
                 bool issue_early = false;
@@ -721,10 +739,10 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 }
                 /* the event kernel re-armed the work counter; a pass never launches more lanes than it has items */
                 const bool last = round == max_rounds - 1;
-                if (last) { int* zf = c.zflag; c.zflag = nullptr; le = ke->step(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; c.zflag = zf; }   /* in-loop events, general kernel */
+                if (last) { int* zf = c.zflag; c.zflag = nullptr; le = flint::launch_step(ke->step, c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; c.zflag = zf; }   /* in-loop events, general kernel */
                 else {
-                    if (try_plane) { le = ke->step_plane(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
-                    if (le == cudaSuccess) { le = ke->step_park(c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                    if (try_plane) { le = flint::launch_step(ke->step_plane, c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
+                    if (le == cudaSuccess) { le = flint::launch_step(ke->step_park, c, dev_sms, n_parked, ex.block, ex.blocks_per_sm, s); g_launches += 1; }
                 }
                 if (issue_early && le == cudaSuccess) {        /* issued after the launch: a pageable destination blocks the host, not the GPU */
                     cudaStream_t s2 = me->pipe_stream[1];
@@ -739,7 +757,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
         };
 
         if (e0) cudaEventRecord(e0, s);
-        cudaError_t le = ke->init(c, grid_all, 128, s);
+        cudaError_t le = flint::launch_kernel(ke->init, c, dim3((unsigned)grid_all), 128, 0, s);
         g_launches += 1;
         if (le == cudaSuccess) le = sweep(nullptr, nullptr, cnt);
         /* ---- InterpOn: trajectories suspended with a full dense store get a new level, 4x as deep, and are resumed ---- */
@@ -778,8 +796,8 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             c.dvo = c.dv; c.dense_eval = 0;
             int* zf = c.zflag;
             c.zflag = (try_plane && ke->dense_plane) ? (int*)(ctr + 3) : nullptr;
-            if (c.zflag) { le = ke->dense_plane(c, grid_all, 128, s); g_launches += 1; }
-            if (le == cudaSuccess) { le = ke->dense_coeffs(c, grid_all, 128, s); g_launches += 1; }
+            if (c.zflag) { le = flint::launch_dense(*ke, true, c, s); g_launches += 1; }
+            if (le == cudaSuccess) { le = flint::launch_dense(*ke, false, c, s); g_launches += 1; }
             c.zflag = zf;
         }
         if (dense) {                                           /* Interpolate runs the dense kernels again (fused path): keep the plane flag */
@@ -1064,13 +1082,14 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
         const flint_sys& sys = *me->sys;
         const flint::KernelEntry* ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, me->events_on);
         if (!ke) ke = flint::find_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, false);
+        if (!ke) ke = flint::get_kernel(me->method, sys.system_id, me->arith == FLINT_ARITH_FMA, false);
         if (!ke) return me->status = fail(FLINT_ERROR, "no kernel compiled for this method / system");
         if (!cuda_ok(flint::launch_interp_validate(a, up, down, s), "interp validate")) return me->status = FLINT_ERROR;
         g_launches += 1;
         KArgs c{};
         fill_static_kargs(me, c);
         c.N = N;
-        ke->load_coefficients(c.coef);
+        flint::load_method_coefficients(me->method, c.coef);
         flint::det_pow_constants(c.powc);
         c.dv = a.dv; c.dense_count = D.dcount;
         c.zflag = me->dense_plane_ok ? D.dzflag : nullptr;
@@ -1094,8 +1113,8 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
             c.dense_eval = 0; c.dvo = tv;
         }
         cudaError_t le = cudaSuccess;
-        if (c.zflag) { le = ke->dense_plane(c, 0, 0, s); g_launches += 1; }
-        if (le == cudaSuccess) { le = ke->dense_coeffs(c, 0, 0, s); g_launches += 1; }
+        if (c.zflag) { le = flint::launch_dense(*ke, true, c, s); g_launches += 1; }
+        if (le == cudaSuccess) { le = flint::launch_dense(*ke, false, c, s); g_launches += 1; }
         if (!cuda_ok(le, "dense kernel launch")) return me->status = FLINT_ERROR;
         if (layout != 0) {
             flint::InterpArgs b = a;

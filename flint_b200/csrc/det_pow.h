@@ -22,9 +22,16 @@
 #ifndef FLINT_B200_DET_POW_H
 #define FLINT_B200_DET_POW_H
 
+#ifdef __CUDACC_RTC__              /* NVRTC (rtc.cu): no host headers; the device branches below use intrinsics only */
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+#else
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #if defined(__CUDACC__)
 #define FLINT_HD __host__ __device__ __forceinline__

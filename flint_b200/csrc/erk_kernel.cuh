@@ -48,9 +48,11 @@
 #ifndef FLINT_B200_ERK_KERNEL_CUH
 #define FLINT_B200_ERK_KERNEL_CUH
 
-#include <type_traits>
 #ifdef FLINT_GANG_TRACE
 #include <cstdio>
+#endif
+#ifndef __CUDACC_RTC__
+#include <type_traits>
 #endif
 #include "erk_methods_gen.cuh"
 #include "systems.cuh"
@@ -66,9 +68,9 @@ constexpr int kMaxSS = FLINT_MAXNUMSTEPSZEVENTS; /* MAXNUMSTEPSZEVENTS, src/ERK.
 
 /* system parameters (flint_sys_create) and, for user functors that declare load_params(const double*, int), the
  * `params` optional of Integrate (src/FLINT_base.f90:400-468; the reference hands it to F on every call) */
-template <class SYS, class = void> struct has_load_params : std::false_type {};
+template <class SYS, class = void> struct has_load_params : meta::false_type {};
 template <class SYS>
-struct has_load_params<SYS, std::void_t<decltype(std::declval<SYS&>().load_params((const double*)nullptr, 0))>> : std::true_type {};
+struct has_load_params<SYS, meta::void_t<decltype(meta::declval<SYS&>().load_params((const double*)nullptr, 0))>> : meta::true_type {};
 template <class SYS> __device__ __forceinline__ void sys_load(SYS& sys, const KArgs& p)
 {
     sys.load(p.sp);
@@ -138,10 +140,10 @@ __device__ __forceinline__ void brent_root(double a, double b, double ya, double
  * Defaults: 128 x 4 with the barrier.  What is being traded (profiles/r01_notes.md): the hot loop is about the size of the
  * 32 KB instruction cache of an SM.  Warps that run it in step share instruction fetches; warps in different phases keep the
  * fp64 pipe busier.  A CTA's warps start together and stay roughly in step on their own; the barrier makes that exact. ---- */
-template <class SYS, class = void> struct has_step_block : std::false_type {};
-template <class SYS> struct has_step_block<SYS, std::void_t<decltype(SYS::STEP_BLOCK)>> : std::true_type {};
-template <class SYS, class = void> struct has_step_barrier : std::false_type {};
-template <class SYS> struct has_step_barrier<SYS, std::void_t<decltype(SYS::STEP_BARRIER)>> : std::true_type {};
+template <class SYS, class = void> struct has_step_block : meta::false_type {};
+template <class SYS> struct has_step_block<SYS, meta::void_t<decltype(SYS::STEP_BLOCK)>> : meta::true_type {};
+template <class SYS, class = void> struct has_step_barrier : meta::false_type {};
+template <class SYS> struct has_step_barrier<SYS, meta::void_t<decltype(SYS::STEP_BARRIER)>> : meta::true_type {};
 template <class SYS> __host__ __device__ constexpr int step_block()
 {
     if constexpr (has_step_block<SYS>::value) return SYS::STEP_BLOCK; else return FLINT_BLOCK_THREADS;
@@ -1136,12 +1138,7 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
 #ifndef FLINT_DENSE_MIN_BLOCKS
 #define FLINT_DENSE_MIN_BLOCKS(METHOD) ((METHOD::NSLOT) <= 12 ? 3 : 2)
 #endif
-constexpr int kDenseBlock = 128;
-template <class METHOD> __host__ __device__ constexpr int dense_smem_doubles(int nI)
-{
-    const int rs = (METHOD::PSTAR + 1) * nI;
-    return kDenseBlock * (rs + (rs & 1)) + 2 * (kDenseBlock + 2);      /* sB, sX, sG (longs) */
-}
+template <class METHOD> __host__ __device__ constexpr int dense_smem_doubles(int nI) { return dense_smem_doubles_ps(METHOD::PSTAR, nI); }
 template <class METHOD, class SYS, bool FMA>
 __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) erk_dense_kernel(const __grid_constant__ KArgs p)
 {
@@ -1235,89 +1232,43 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     }
 }
 
-/* Host-side launchers shared by all instantiations (inst_*.cu). */
+#ifndef __CUDACC_RTC__
+/* Host side: the table entry of one instantiation (inst_*.cu; kargs.h: KernelEntry).  The launchers themselves are not
+ * templates (registry.cu): they take the entry points and the compile-time facts collected here, so that kernels NVRTC builds
+ * at run time from a user's source (rtc.cu) are launched by the same code. */
 template <class METHOD, class SYS, bool FMA, int EVMODE>
-cudaError_t launch_step(const KArgs& a, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t s)
+StepKernel step_kernel_entry()
 {
-    constexpr int smem = kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>();
-    constexpr int BLOCK = step_block<SYS>();
-    int block = (block_req > 0 && block_req < BLOCK) ? (block_req + 31) / 32 * 32 : BLOCK;
-    if (smem > 0) block = BLOCK;                            /* the shared-memory layout is compiled for this block size */
-    if (smem > 48 * 1024) {                                 /* per device context, and cheap: not cached */
-        const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
-    /* one occupancy query per (device, CTA size) and host thread: handles on different devices may launch from different threads */
-    static thread_local int cached_block = -1, cached_bps = 0, cached_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cached_block != block || cached_dev != dev) {
-        int q = 0;
-        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, erk_step_kernel<METHOD, SYS, FMA, EVMODE>, block, smem);
-        if (e != cudaSuccess) return e;
-        cached_bps = q < 1 ? 1 : q;
-        cached_block = block; cached_dev = dev;
-    }
-    int bps = cached_bps;
-    if (bps_req > 0 && bps_req < bps) bps = bps_req;
-    long grid = (long)sm_count * bps;                       /* persistent lanes: one resident wave */
-    const long need = (n_items + block - 1) / block;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    if constexpr (EVMODE != 1) {
-        /* small shards: more than one but fewer than ~8 trajectories per lane -> the gang-scheduled kernel (see erk_step_kernel) */
-        const long lanes = grid * block;
-        int S = 0;
-        if (a.round_req >= 2) S = a.round_req;
-        else if (a.round_req == 0 && a.n_items_exact && n_items > lanes && n_items < 8 * lanes) S = n_items < 4 * lanes ? 64 : 128;
-        if (S > 4096) S = 4096;
-        if (S >= 2 && a.n_items_exact) {
-            const long per = (n_items + grid - 1) / grid;
-            const long smem2 = smem + ((per + 1) & ~1L) * 4 + (long)block * 4;
-            if (smem2 <= 200 * 1024) {
-                KArgs b = a;
-                b.round_len = S;
-                if (smem2 > 48 * 1024) {
-                    const cudaError_t e = cudaFuncSetAttribute(erk_step_kernel<METHOD, SYS, FMA, EVMODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-                    if (e != cudaSuccess) return e;
-                }
-                erk_step_kernel<METHOD, SYS, FMA, EVMODE, true><<<(unsigned)grid, block, (size_t)smem2, s>>>(b);
-                return cudaGetLastError();
-            }
-        }
-    }
-    erk_step_kernel<METHOD, SYS, FMA, EVMODE><<<(unsigned)grid, block, smem, s>>>(a);
-    return cudaGetLastError();
+    StepKernel k{};
+    k.classic = (const void*)&erk_step_kernel<METHOD, SYS, FMA, EVMODE, false>;
+    if constexpr (EVMODE != 1) k.gang = (const void*)&erk_step_kernel<METHOD, SYS, FMA, EVMODE, true>;
+    k.block = step_block<SYS>();
+    k.smem = kstore_smem_bytes<METHOD, SYS, METHOD::SMEM_SLOTS>();
+    return k;
 }
-template <class METHOD, class SYS, bool FMA>
-cudaError_t launch_init(const KArgs& a, int grid, int block, cudaStream_t s)
+/* SYSZ: the plane variant of SYS (systems.cuh: zc), or SYS itself when it has none */
+template <class METHOD, class SYS, class SYSZ, bool FMA, bool EVENTS>
+KernelEntry kernel_entry()
 {
-    erk_init_kernel<METHOD, SYS, FMA><<<grid, block, 0, s>>>(a);
-    return cudaGetLastError();
-}
-template <class METHOD, class SYS, bool FMA>
-cudaError_t launch_event(const KArgs& a, int grid, int block, cudaStream_t s)
-{
-    erk_event_kernel<METHOD, SYS, FMA><<<grid, block, 0, s>>>(a);
-    return cudaGetLastError();
-}
-/* grid = (trajectories, blocks of 128 steps up to the store's capacity); blocks beyond a trajectory's step count return at once */
-template <class METHOD, class SYS, bool FMA>
-cudaError_t launch_dense(const KArgs& a, int /*grid*/, int /*block*/, cudaStream_t s)
-{
-    const long cap = a.dv.capacity();
-    long gy = (cap + kDenseBlock - 1) / kDenseBlock;
-    if (gy < 1) gy = 1;
-    if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const int smem = a.dense_eval ? dense_smem_doubles<METHOD>(a.nI) * 8 : 0;
-    if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(erk_dense_kernel<METHOD, SYS, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
+    KernelEntry e{};
+    e.method = METHOD::ID; e.system = SYS::ID; e.fma = FMA; e.events = EVENTS;
+    e.init = (const void*)&erk_init_kernel<METHOD, SYS, FMA>;
+    e.step = step_kernel_entry<METHOD, SYS, FMA, EVENTS ? 1 : 0>();
+    if constexpr (EVENTS) {
+        e.step_park = step_kernel_entry<METHOD, SYS, FMA, 2>();
+        e.event = (const void*)&erk_event_kernel<METHOD, SYS, FMA>;
     }
-    erk_dense_kernel<METHOD, SYS, FMA><<<dim3((unsigned)a.N, (unsigned)gy), kDenseBlock, smem, s>>>(a);
-    return cudaGetLastError();
+    e.dense_coeffs = (const void*)&erk_dense_kernel<METHOD, SYS, FMA>;
+    if constexpr (SYS::ZPLANE != 0u && !std::is_same<SYS, SYSZ>::value) {
+        e.step_plane = step_kernel_entry<METHOD, SYSZ, FMA, EVENTS ? 2 : 0>();
+        e.dense_plane = (const void*)&erk_dense_kernel<METHOD, SYSZ, FMA>;
+    }
+    e.pstar = METHOD::PSTAR;
+    e.n_state_doubles = SD<SYS::N, SYS::M_MAX>::COUNT; e.n_state_ints = SI::COUNT;
+    e.sys_n = SYS::N; e.sys_m_max = SYS::M_MAX;
+    return e;
 }
-template <class METHOD> void load_method_coefficients(double* dst) { METHOD::load_coefficients(*(double (*)[FLINT_NCOEF])dst); }
+#endif
 
 }  // namespace flint
 #endif

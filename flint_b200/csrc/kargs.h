@@ -2,7 +2,9 @@
 #ifndef FLINT_B200_KARGS_H
 #define FLINT_B200_KARGS_H
 
+#ifndef __CUDACC_RTC__              /* NVRTC (rtc.cu) declares the runtime's device-side types itself */
 #include <cuda_runtime.h>
+#endif
 #include "../../include/flint_b200.h"
 
 #ifndef FLINT_BLOCK_THREADS
@@ -133,6 +135,14 @@ struct KArgs {
     double powc[32];             /* constants of the controller's pow (arith.cuh: det_pow_constants) */
 };
 
+/* erk_dense_kernel: CTA = 128 consecutive steps of one trajectory; shared memory of its fused evaluation (sB, sX, sG) in doubles */
+constexpr int kDenseBlock = 128;
+__host__ __device__ constexpr int dense_smem_doubles_ps(int pstar, int nI)
+{
+    const int rs = (pstar + 1) * nI;
+    return kDenseBlock * (rs + (rs & 1)) + 2 * (kDenseBlock + 2);
+}
+
 struct InterpArgs {
     long N, G;
     int nI, pstar;
@@ -144,6 +154,7 @@ struct InterpArgs {
     int fma;
     long chunk; int nchunks;         /* filled by launch_interp */
 };
+#ifndef __CUDACC_RTC__             /* ---- host side: launchers and the table of integrate kernels ---- */
 cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
 /* per-trajectory validation of the grid (src/ERKInterp.f90:60-76) against any kind of records */
 cudaError_t launch_interp_validate(const InterpArgs&, int grid_up, int grid_down, cudaStream_t);
@@ -152,22 +163,27 @@ cudaError_t launch_dense_slots(int* slot, const int* list, long n, cudaStream_t)
 cudaError_t launch_set_counters(unsigned long long* ctr, unsigned long long c0, unsigned long long c1, unsigned long long c2,
                                 unsigned long long c3, cudaStream_t);   /* registry.cu */
 
-/* registry of compiled integrate kernels (filled by static initialisers in inst_*.cu) */
-typedef cudaError_t (*launch_fn)(const KArgs&, int grid, int block, cudaStream_t);
-/* the persistent step kernels size themselves: one resident wave of the device (SM count x resident CTAs of the kernel's own
- * CTA size, erk_kernel.cuh: StepCfg), never more lanes than items; block_req / bps_req > 0 lower the CTA size / the CTAs per SM */
-typedef cudaError_t (*step_launch_fn)(const KArgs&, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t);
+/* The integrate kernels of one (method, system, arithmetic, events) combination, as the launchers see them: entry points that
+ * cudaLaunchKernel accepts -- the host stub of a kernel compiled into the library (inst_*.cu) or the cudaKernel_t of a module
+ * NVRTC built at run time from a user's source (rtc.cu) -- plus the compile-time facts the launch needs.  One code path launches
+ * both. */
+struct StepKernel {              /* one erk_step_kernel variant (event mode, plane / general) */
+    const void* classic;         /* persistent lanes, one trajectory per lane at a time */
+    const void* gang;            /* gang-scheduled rounds (small shards); NULL: not instantiated (EVMODE 1) */
+    int block;                   /* CTA size the kernel was compiled for (__launch_bounds__; the shared-memory KStore is laid out for it) */
+    int smem;                    /* bytes of dynamic shared memory of the KStore */
+};
 struct KernelEntry {
     int method, system;
     bool fma, events;
-    launch_fn init;              /* erk_init_kernel */
-    step_launch_fn step;         /* erk_step_kernel, EVMODE 0 (events == false) or 1 (events located in the lane loop) */
-    step_launch_fn step_park;    /* erk_step_kernel, EVMODE 2 (NULL when events == false) */
-    launch_fn event;             /* erk_event_kernel (NULL when events == false) */
-    launch_fn dense_coeffs;      /* erk_dense_kernel: dense-output coefficients from the step logs */
-    step_launch_fn step_plane;   /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; NULL if none */
-    launch_fn dense_plane;       /* plane variant of `dense_coeffs`; NULL if none */
-    void (*load_coefficients)(double* dst);
+    const void* init;            /* erk_init_kernel */
+    StepKernel step;             /* EVMODE 0 (events == false) or 1 (events located in the lane loop) */
+    StepKernel step_park;        /* EVMODE 2 (classic == NULL when events == false) */
+    const void* event;           /* erk_event_kernel (NULL when events == false) */
+    const void* dense_coeffs;    /* erk_dense_kernel: dense-output coefficients from the step logs */
+    StepKernel step_plane;       /* plane variant (SYS::zc) of `step` for EVMODE 0, of `step_park` for events; classic == NULL if none */
+    const void* dense_plane;     /* plane variant of `dense_coeffs`; NULL if none */
+    int pstar;                   /* METHOD::PSTAR (shared memory of the fused dense kernel) */
     int n_state_doubles, n_state_ints;
     int sys_n, sys_m_max;        /* SYS::N, SYS::M_MAX (validation of user systems in flint_sys_create) */
 };
@@ -175,6 +191,17 @@ void register_kernel(const KernelEntry&);
 const KernelEntry* find_kernel(int method, int system, bool fma, bool events);
 const KernelEntry* find_system(int system);          /* any entry of that system, or NULL */
 int kernel_count();
+void load_method_coefficients(int method, double* dst);   /* Butcher / error / dense coefficients into KArgs::coef */
+
+/* grid x block threads of kernel k with the parameter block by value */
+cudaError_t launch_kernel(const void* k, const KArgs&, dim3 grid, int block, size_t smem, cudaStream_t);
+/* the persistent step kernels size themselves: one resident wave of the device (SM count x resident CTAs of the kernel's own
+ * CTA size), never more lanes than items; block_req / bps_req > 0 lower the CTA size / the CTAs per SM.  Chooses the
+ * gang-scheduled variant for small shards (erk_kernel.cuh). */
+cudaError_t launch_step(const StepKernel&, const KArgs&, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t);
+/* erk_dense_kernel: grid = (trajectories, blocks of 128 steps up to the store's capacity) */
+cudaError_t launch_dense(const KernelEntry&, bool plane, const KArgs&, cudaStream_t);
+#endif
 
 }  // namespace flint
 #endif

@@ -1,28 +1,139 @@
-/* registry.cu -- table of the integrate kernels compiled into the library. */
+/* registry.cu -- table of the integrate kernels (compiled into the library by inst_*.cu, or built at run time by rtc.cu) and
+ * the launchers they share. */
+#include <mutex>
 #include <vector>
 #include "kargs.h"
+#include "erk_methods_gen.cuh"
 
 namespace flint {
 
-static std::vector<KernelEntry>& table()
+/* entries are added by static initialisers and, later, by run-time registration from any host thread; they are never removed
+ * and never move (heap nodes), so the pointers find_kernel returns stay valid */
+static std::mutex& table_mutex()
 {
-    static std::vector<KernelEntry> t;
+    static std::mutex m;
+    return m;
+}
+static std::vector<KernelEntry*>& table()
+{
+    static std::vector<KernelEntry*> t;
     return t;
 }
-void register_kernel(const KernelEntry& e) { table().push_back(e); }
+void register_kernel(const KernelEntry& e)
+{
+    std::lock_guard<std::mutex> g(table_mutex());
+    table().push_back(new KernelEntry(e));
+}
 const KernelEntry* find_kernel(int method, int system, bool fma, bool events)
 {
-    for (const KernelEntry& e : table())
-        if (e.method == method && e.system == system && e.fma == fma && e.events == events) return &e;
+    std::lock_guard<std::mutex> g(table_mutex());
+    for (const KernelEntry* e : table())
+        if (e->method == method && e->system == system && e->fma == fma && e->events == events) return e;
     return nullptr;
 }
 const KernelEntry* find_system(int system)
 {
-    for (const KernelEntry& e : table())
-        if (e.system == system) return &e;
+    std::lock_guard<std::mutex> g(table_mutex());
+    for (const KernelEntry* e : table())
+        if (e->system == system) return e;
     return nullptr;
 }
-int kernel_count() { return (int)table().size(); }
+int kernel_count()
+{
+    std::lock_guard<std::mutex> g(table_mutex());
+    return (int)table().size();
+}
+void load_method_coefficients(int method, double* dst)
+{
+    double (&d)[FLINT_NCOEF] = *(double (*)[FLINT_NCOEF])dst;
+    switch (method) {
+    case ERK_DOP54: MethodDOP54::load_coefficients(d); break;
+    case ERK_VERNER98R: MethodVerner98R::load_coefficients(d); break;
+    case ERK_VERNER65E: MethodVerner65E::load_coefficients(d); break;
+    default: MethodDOP853::load_coefficients(d); break;
+    }
+}
+
+/* ---- launchers (kargs.h) ---- */
+cudaError_t launch_kernel(const void* k, const KArgs& a, dim3 grid, int block, size_t smem, cudaStream_t s)
+{
+    void* args[1] = {const_cast<KArgs*>(&a)};
+    return cudaLaunchKernel(k, grid, dim3((unsigned)block), args, smem, s);
+}
+
+/* resident CTAs per SM of kernel k at this CTA size: one occupancy query per (kernel, CTA size, device) and host thread --
+ * handles on different devices launch from different threads */
+static cudaError_t resident_ctas(const void* k, int block, int smem, int* out)
+{
+    struct Key { const void* k; int block, smem, dev, bps; };
+    static thread_local std::vector<Key> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Key& c : cache)
+        if (c.k == k && c.block == block && c.smem == smem && c.dev == dev) { *out = c.bps; return cudaSuccess; }
+    int q = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k, block, (size_t)smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) q = 1;
+    cache.push_back(Key{k, block, smem, dev, q});
+    *out = q;
+    return cudaSuccess;
+}
+
+cudaError_t launch_step(const StepKernel& k, const KArgs& a, int sm_count, long n_items, int block_req, int bps_req, cudaStream_t s)
+{
+    const int smem = k.smem, BLOCK = k.block;
+    int block = (block_req > 0 && block_req < BLOCK) ? (block_req + 31) / 32 * 32 : BLOCK;
+    if (smem > 0) block = BLOCK;                            /* the shared-memory layout is compiled for this block size */
+    if (smem > 48 * 1024) {                                 /* per device context, and cheap: not cached */
+        const cudaError_t e = cudaFuncSetAttribute(k.classic, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    int bps = 1;
+    { const cudaError_t e = resident_ctas(k.classic, block, smem, &bps); if (e != cudaSuccess) return e; }
+    if (bps_req > 0 && bps_req < bps) bps = bps_req;
+    long grid = (long)sm_count * bps;                       /* persistent lanes: one resident wave */
+    const long need = (n_items + block - 1) / block;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (k.gang) {
+        /* small shards: more than one but fewer than ~8 trajectories per lane -> the gang-scheduled kernel (see erk_step_kernel) */
+        const long lanes = grid * block;
+        int S = 0;
+        if (a.round_req >= 2) S = a.round_req;
+        else if (a.round_req == 0 && a.n_items_exact && n_items > lanes && n_items < 8 * lanes) S = n_items < 4 * lanes ? 64 : 128;
+        if (S > 4096) S = 4096;
+        if (S >= 2 && a.n_items_exact) {
+            const long per = (n_items + grid - 1) / grid;
+            const long smem2 = smem + ((per + 1) & ~1L) * 4 + (long)block * 4;
+            if (smem2 <= 200 * 1024) {
+                KArgs b = a;
+                b.round_len = S;
+                if (smem2 > 48 * 1024) {
+                    const cudaError_t e = cudaFuncSetAttribute(k.gang, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                    if (e != cudaSuccess) return e;
+                }
+                return launch_kernel(k.gang, b, dim3((unsigned)grid), block, (size_t)smem2, s);
+            }
+        }
+    }
+    return launch_kernel(k.classic, a, dim3((unsigned)grid), block, (size_t)smem, s);
+}
+
+cudaError_t launch_dense(const KernelEntry& e, bool plane, const KArgs& a, cudaStream_t s)
+{
+    const void* k = plane ? e.dense_plane : e.dense_coeffs;
+    const long cap = a.dv.capacity();
+    long gy = (cap + kDenseBlock - 1) / kDenseBlock;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    const int smem = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : 0;
+    if (smem > 48 * 1024) {
+        const cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (er != cudaSuccess) return er;
+    }
+    return launch_kernel(k, a, dim3((unsigned)a.N, (unsigned)gy), kDenseBlock, (size_t)smem, s);
+}
 
 /* work counters of one Integrate chunk, written in stream order (a pageable host-to-device copy would make the host wait
  * for everything already queued on the stream) */

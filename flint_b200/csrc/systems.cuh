@@ -29,7 +29,6 @@
 #ifndef FLINT_B200_SYSTEMS_CUH
 #define FLINT_B200_SYSTEMS_CUH
 
-#include <type_traits>
 #include "arith.cuh"
 #include "../../include/flint_b200.h"
 
@@ -268,7 +267,7 @@ struct SysLorenz {
         f[2] = madd<FMA>(y[0], y[1], -(beta * y[2]));
     }
     template <bool FMA>
-    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<std::remove_cv_t<std::remove_reference_t<decltype(*this)>>>(y, o, f); }
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<meta::remove_cvref_t<decltype(*this)>>(y, o, f); }
     template <bool FMA>
     __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&)[N], unsigned, double (&)[M_MAX], int (&)[M_MAX], int, int&) const {}
@@ -310,7 +309,7 @@ struct SysTwoBody {
         f[0] = fac * y[0]; f[1] = fac * y[1]; f[2] = fac * y[2];
     }
     template <bool FMA>
-    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<std::remove_cv_t<std::remove_reference_t<decltype(*this)>>>(y, o, f); }
+    __device__ __forceinline__ void assemble(const double (&y)[N], const double (&o)[NOUT], double (&f)[N]) const { scatter_rhs<meta::remove_cvref_t<decltype(*this)>>(y, o, f); }
     template <bool FMA>
     __device__ __forceinline__ void rhs(double, const double (&y)[N], double (&f)[N]) const { eval_rhs<FMA>(*this, y, f); }
     __device__ __forceinline__ void events(int, double, double (&y)[N], unsigned eval_bits, double (&value)[M_MAX],

@@ -56,7 +56,8 @@ enum {
     FLINT_SYS_CR3BP_SPATIAL = 2, /* tests/test_WP.f90:88-109      sysparams = {mu}              n = 6 */
     FLINT_SYS_LORENZ = 3,        /* tests/test_Lorenz.f90:45-57   sysparams = {sigma,rho,beta}  n = 3 */
     FLINT_SYS_TWOBODY = 4,       /* tests/test_TBP.f90:46-59      sysparams = {GM}              n = 6 */
-    FLINT_SYS_USER_BASE = 100    /* ids >= 100: functors registered at build time (csrc/systems.cuh "user systems");
+    FLINT_SYS_USER_BASE = 100    /* ids >= 100: user functors, registered at build time (csrc/systems.cuh "user systems") or at
+                                    run time from their source (flint_sys_register_source);
                                     their event sets are numbered by the functor itself, m <= its M_MAX */
 };
 enum {
@@ -185,6 +186,19 @@ long flint_b200_shard_indices(long N, int n_shards, int shard, long chunk, long*
 /* ---- DiffEqSys ---- */
 flint_sys_t* flint_sys_create(int system_id, int eventset_id, int n, int m, const double* sysparams, int nsysparams);
 void flint_sys_destroy(flint_sys_t*);
+/* Run-time registration of a user DiffEqSys (the reference's user extends DiffEqSys with F and G, src/FLINT_base.f90:220-309; here
+ * they are device functors).  `source`: the text of a header that defines `struct <struct_name> : flint::UserSystem<n, m_max>` in
+ * namespace flint with `static constexpr int ID = FLINT_SYS_USER_BASE + k`, `load`, `accel<FMA>` (F) and, if has_events, `events`
+ * (G) -- the same text a build-time user header holds (flint_b200/csrc/systems.cuh; tests/user_systems/).  NVRTC compiles it
+ * against the kernel headers embedded in the library, with the library's own options; the integrate kernels of a (method,
+ * arithmetic, events) combination are built on first use and cached on disk ($FLINT_B200_RTC_CACHE, default
+ * $HOME/.cache/flint_b200).  Needs libnvrtc at run time (dlopen; $FLINT_B200_NVRTC overrides the search), no GPU for the
+ * registration itself.  Returns FLINT_SUCCESS and the id for flint_sys_create, else FLINT_ERROR_PARAMS / FLINT_ERROR_DIMENSION /
+ * FLINT_ERROR with the compiler's log in flint_last_error(). */
+int flint_sys_register_source(const char* struct_name, const char* source, int has_events, int* system_id_out);
+/* Compiles and caches the integrate kernels of one (method, arithmetic, events) combination of a system registered from source,
+ * without loading them (no GPU needed): warms the cache ahead of the first Integrate. */
+int flint_sys_precompile(int system_id, int method, int arith, int events_on);
 
 /* ---- ERK_class ---- */
 flint_erk_t* flint_erk_create(void);

@@ -324,3 +324,61 @@ def test_per_trajectory_grids():
                 so, yo = sc.interpolate(grids[t], save=True)
                 assert so == 0
                 K.assert_bit_equal(yarr[t], yo, "per-trajectory grid, trajectory %d" % t)
+
+
+# ------------------------------------------------------------------------------------------------ run-time registered systems
+def test_runtime_registered_systems(tmp_path, monkeypatch):
+    """user F / G handed to the STOCK library as source at run time (flint_sys_register_source; NVRTC, csrc/rtc.cu).
+    The run-time Lorenz functor equals the oracle's Lorenz bit for bit (all launch paths: persistent lanes, gang-scheduled rounds,
+    two shards, dense output + fused Interpolate); a Van der Pol oscillator with an upward zero-crossing event agrees with scipy's
+    DOP853, with mu from the system parameters and from Integrate(params=...)."""
+    import os
+    from scipy.integrate import solve_ivp
+    monkeypatch.setenv("FLINT_B200_RTC_CACHE", str(tmp_path))
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "user_systems", "runtime_systems.cuh")).read()
+    RT_LORENZ = F.register_system_source("RtLorenz", src, False)
+    RT_VDP = F.register_system_source("RtVanDerPol", src, True)
+    n0 = F.lib().flint_b200_kernel_count()
+    for method, arith in ((F.ERK_DOP54, 0), (F.ERK_DOP853, 1), (F.ERK_VERNER98R, 0), (F.ERK_VERNER65E, 1)):
+        case = K.lorenz_case(method, 1e-10, arith, xf=8.0)
+        y0 = P.lorenz_ensemble(300)
+        o = case.run_oracle(y0)
+        sys_ = F.DiffEqSys(RT_LORENZ, F.FLINT_EVSET_NONE, list(P.LORENZ_PARAMS), n=3, m=0)
+        erk = F.ERK()
+        assert erk.Init(sys_, case.max_steps, Method=method, ATol=[case.atol], RTol=[case.rtol], Arith=arith) == 0
+        for kw in (dict(), dict(round_len=16), dict(devices=[0, 0], shard_chunk=64)):
+            g = erk.IntegrateBatch(0.0, y0, 8.0, StepSz=0.0, StiffTest=0, **kw)
+            for a, b, what in ((g["Yf"], o["yf"], "Yf"), (g["counters"], o["counters"], "counters"), (g["status"], o["status"], "status")):
+                K.assert_bit_equal(a, b, "run-time Lorenz %s %r %s" % (MNAME[method], kw, what))
+    assert F.lib().flint_b200_kernel_count() == n0 + 4
+    # dense output of a run-time system: coefficients rebuilt from the step logs by the run-time module's own dense kernel
+    case = K.lorenz_case(F.ERK_DOP853, 1e-9, 0, xf=3.0, interp_on=True)
+    y0 = P.lorenz_ensemble(64)
+    xarr = np.linspace(0.0, 3.0, 301)
+    o = case.run_oracle(y0, xarr=xarr)
+    sys_ = F.DiffEqSys(RT_LORENZ, F.FLINT_EVSET_NONE, list(P.LORENZ_PARAMS), n=3, m=0)
+    for dense_mode in (0, 1):
+        erk = F.ERK()
+        assert erk.Init(sys_, case.max_steps, Method=F.ERK_DOP853, ATol=[case.atol], RTol=[case.rtol], InterpOn=True) == 0
+        g = erk.IntegrateBatch(0.0, y0, 3.0, StepSz=0.0, StiffTest=0, dense_mode=dense_mode)
+        st, yarr, ist = erk.InterpolateBatch(xarr, 64)
+        assert st == 0 and (ist == 0).all()
+        K.assert_bit_equal(yarr, o["yarr"], "run-time Lorenz dense output, dense_mode %d" % dense_mode)
+    # Van der Pol with an event, against scipy
+    mu, xf, N = 1.5, 20.0, 64
+    y0 = np.stack([2.0 + 1e-3 * P.uniform01(np.arange(N), 5), np.zeros(N)])
+    up = lambda t, y: y[0]  # noqa: E731
+    up.direction = 1
+    for sp, params in (([mu], None), ([0.3], [mu])):
+        sys_ = F.DiffEqSys(RT_VDP, 1, sp, n=2, m=1)
+        erk = F.ERK()
+        assert erk.Init(sys_, 100000, Method=F.ERK_DOP853, ATol=[1e-13], RTol=[1e-12], EventsOn=True, EventTol=[1e-11]) == 0
+        g = erk.IntegrateBatch(0.0, y0, xf, StepSz=0.0, EventStates=True, MaxEvents=8, params=params)
+        assert (g["status"] == 0).all()
+        for i in (0, 17, 63):
+            r = solve_ivp(lambda t, y: [y[1], mu * (1 - y[0] ** 2) * y[1] - y[0]], (0.0, xf), y0[:, i], method="DOP853", rtol=1e-12, atol=1e-13, events=up)
+            assert np.allclose(g["Yf"][:, i], r.y[:, -1], rtol=0, atol=1e-8), (g["Yf"][:, i], r.y[:, -1])
+            te = r.t_events[0]
+            assert g["nEvents"][i] == len(te), (g["nEvents"][i], len(te))
+            assert np.allclose(g["EventStates"][0, :len(te), i], te, rtol=0, atol=1e-8)
+            assert (g["EventStates"][3, :len(te), i] == 1.0).all()

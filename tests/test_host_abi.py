@@ -250,3 +250,38 @@ def test_abi_structs_agree_between_c_header_ctypes_and_fortran():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "s.c"), "-o", os.path.join(td, "s")], check=True)
         sizes = [int(v) for v in subprocess.run([os.path.join(td, "s")], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(api._Exec), C.sizeof(api._InitOpts), C.sizeof(api._IntOpts)]
+
+
+RT_SOURCE = os.path.join(ROOT, "tests", "user_systems", "runtime_systems.cuh")
+
+
+def test_runtime_registration_from_source_host_side(tmp_path, monkeypatch):
+    """flint_sys_register_source (csrc/rtc.cu): a user functor's SOURCE is compiled by NVRTC against the kernel
+    headers embedded in the library.  Registration needs no GPU: the functor's n / m_max / id come back from the compiled probe,
+    flint_sys_create validates against them, a source that does not compile returns the compiler's log, an id cannot be taken
+    twice, and flint_sys_precompile builds + caches the integrate kernels' cubin."""
+    monkeypatch.setenv("FLINT_B200_RTC_CACHE", str(tmp_path))
+    src = open(RT_SOURCE).read()
+    assert F.register_system_source("RtLorenz", src, False) == F.FLINT_SYS_USER_BASE + 10
+    assert F.register_system_source("RtVanDerPol", src, True) == F.FLINT_SYS_USER_BASE + 11
+    assert F.register_system_source("RtLorenz", src, False) == F.FLINT_SYS_USER_BASE + 10           # idempotent
+    F.DiffEqSys(F.FLINT_SYS_USER_BASE + 10, F.FLINT_EVSET_NONE, [10.0, 28.0, 8.0 / 3.0], n=3, m=0)
+    F.DiffEqSys(F.FLINT_SYS_USER_BASE + 11, 1, [1.5], n=2, m=1)
+    for bad in (dict(system_id=F.FLINT_SYS_USER_BASE + 10, n=4, m=0), dict(system_id=F.FLINT_SYS_USER_BASE + 10, n=3, m=1),
+                dict(system_id=F.FLINT_SYS_USER_BASE + 11, n=2, m=2), dict(system_id=F.FLINT_SYS_USER_BASE + 12, n=3, m=0)):
+        with pytest.raises(ValueError):
+            F.DiffEqSys(bad["system_id"], F.FLINT_EVSET_NONE if bad["m"] == 0 else 1, [1.0], n=bad["n"], m=bad["m"])
+    with pytest.raises(ValueError, match="different source"):
+        F.register_system_source("RtLorenz", src + "\n/* changed */\n", False)
+    broken = src.replace("RtLorenz", "RtBroken").replace("USER_BASE + 10", "USER_BASE + 13").replace("sigma * (y[1] - y[0]);", "sigma * (y[1] - y[0])")
+    with pytest.raises(ValueError, match="expected a \";\""):
+        F.register_system_source("RtBroken", broken, False)
+    with pytest.raises(ValueError):
+        F.register_system_source("NoSuchStruct", src, False)
+    with pytest.raises(ValueError, match="no event function"):
+        F.precompile_system(F.FLINT_SYS_USER_BASE + 10, F.ERK_DOP853, 0, True)
+    F.precompile_system(F.FLINT_SYS_USER_BASE + 11, F.ERK_DOP54, F.FLINT_ARITH_FMA, True)
+    blobs = [f for f in os.listdir(tmp_path) if f.startswith("rt_") and f.endswith(".bin")]
+    assert len(blobs) == 1 and os.path.getsize(os.path.join(tmp_path, blobs[0])) > 100000
+    F.precompile_system(F.FLINT_SYS_USER_BASE + 11, F.ERK_DOP54, F.FLINT_ARITH_FMA, True)            # served from the cache
+    assert len(os.listdir(tmp_path)) == 1
