@@ -78,13 +78,13 @@ FLINT_SHARD_CHUNK = 4096
 class _Exec(C.Structure):
     _fields_ = [("mem", C.c_int), ("device", C.c_int), ("stream", C.c_void_p), ("async_", C.c_int),
                 ("dense_cap", C.c_long), ("block_threads", C.c_int), ("blocks_per_sm", C.c_int), ("event_mode", C.c_int), ("plane_variant", C.c_int), ("pipeline", C.c_int),
-                ("round_len", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * FLINT_MAX_DEVICES), ("shard_chunk", C.c_long), ("dense_mode", C.c_int)]
+                ("round_len", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * FLINT_MAX_DEVICES), ("shard_chunk", C.c_long), ("dense_mode", C.c_int), ("dense_spill", C.c_int)]
 
 
 def _exec(mem, device=0, stream=None, async_=0, dense_cap=0, block_threads=0, blocks_per_sm=0, event_mode=0, plane_variant=0,
-          pipeline=0, round_len=0, devices=None, shard_chunk=0, dense_mode=0):
+          pipeline=0, round_len=0, devices=None, shard_chunk=0, dense_mode=0, dense_spill=0):
     ex = _Exec()
-    ex.dense_mode = int(dense_mode)
+    ex.dense_mode, ex.dense_spill = int(dense_mode), int(dense_spill)
     ex.mem, ex.device, ex.stream, ex.async_, ex.dense_cap = int(mem), int(device), stream, int(async_), int(dense_cap)
     ex.block_threads, ex.blocks_per_sm, ex.event_mode, ex.plane_variant = int(block_threads), int(blocks_per_sm), int(event_mode), int(plane_variant)
     ex.pipeline, ex.round_len, ex.shard_chunk = int(pipeline), int(round_len), int(shard_chunk)
@@ -356,7 +356,8 @@ class ERK:
     def IntegrateBatch(self, X0, Y0, Xf, StepSz=None, UseConstStepSz=None, StepAdvance=None, IntStepsOn=None,
                        EventMask=None, EventStates=False, StiffTest=None, params=None, MaxEvents=4, StepsCap=None,
                        out=None, device=0, stream=None, dense_cap=0, block_threads=0, blocks_per_sm=0, want_counters=True,
-                       event_mode=0, plane_variant=0, async_=False, pipeline=0, round_len=0, devices=None, shard_chunk=0, dense_mode=0):
+                       event_mode=0, plane_variant=0, async_=False, pipeline=0, round_len=0, devices=None, shard_chunk=0, dense_mode=0,
+                       dense_spill=0):
         """Y0: (n, N) structure-of-arrays, numpy (host buffers: the call stages H2D/D2H itself) or a
         torch CUDA tensor (device buffers: nothing is copied).  Xf scalar or (N,).  Returns a dict of
         SoA outputs (numpy or torch, matching the input kind).  async_ (device buffers only): return after enqueueing
@@ -417,7 +418,7 @@ class ERK:
             ev = _EventsOut(MaxEvents, _ptr(rec), _ptr(ecount))
             res.update(EventStates=rec, nEvents=ecount)
         ex = _exec(FLINT_MEM_DEVICE if on_dev else FLINT_MEM_HOST, device, stream, int(bool(async_) and on_dev), dense_cap,
-                   block_threads, blocks_per_sm, event_mode, plane_variant, pipeline, round_len, devices, shard_chunk, dense_mode)
+                   block_threads, blocks_per_sm, event_mode, plane_variant, pipeline, round_len, devices, shard_chunk, dense_mode, dense_spill)
         x0s = float(X0) if x0v is None else 0.0
         st = lib().flint_erk_integrate_batch(self._h, N, x0s, _ptr(x0v), _ptr(Y0), _ptr(xf), _ptr(yf), _ptr(h), C.byref(io),
                                              _ptr(counters), _ptr(status), C.byref(steps) if steps else None,

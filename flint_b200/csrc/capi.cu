@@ -82,8 +82,93 @@ struct DenseStore {
     int* slot[FLINT_DENSE_LEVELS] = {nullptr};
     int* dcount = nullptr;
     int* dzflag = nullptr;             /* device word: 1 = every trajectory lies in the system's invariant plane (plane-variant kernels) */
+    /* flint_exec.dense_spill: between Integrate and Interpolate the store of a part of the ensemble waits in host memory (the
+     * reference's Xint / Bip are host arrays, src/ERKInit.f90:321-332); spilled = the device copy is gone, hbase etc. hold it */
+    bool spilled = false;
+    double* hbase[FLINT_DENSE_LEVELS] = {nullptr};
+    int* hslot[FLINT_DENSE_LEVELS] = {nullptr};
+    int* hdcount = nullptr;
+    int hzflag[2] = {0, 0};
+    bool hpinned = false;
+    void* host_alloc(size_t bytes)
+    {
+        void* p = nullptr;
+        if (hpinned) { if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p; cudaGetLastError(); return nullptr; }
+        return malloc(bytes);
+    }
+    void host_free(void* p) { if (!p) return; if (hpinned) cudaFreeHost(p); else free(p); }
+    void release_host()
+    {
+        for (int l = 0; l < FLINT_DENSE_LEVELS; ++l) { host_free(hbase[l]); host_free(hslot[l]); hbase[l] = nullptr; hslot[l] = nullptr; }
+        host_free(hdcount); hdcount = nullptr; spilled = false;
+    }
+    void release_device()
+    {
+        if (dzflag) cudaFree(dzflag);
+        dzflag = nullptr;
+        for (int l = 0; l < FLINT_DENSE_LEVELS; ++l) {
+            if (base[l]) cudaFree(base[l]);
+            if (slot[l]) cudaFree(slot[l]);
+            base[l] = nullptr; slot[l] = nullptr;
+        }
+        if (dcount) cudaFree(dcount);
+        dcount = nullptr;
+    }
+    size_t level_bytes(int l) const { return (size_t)rows[l] * (size_t)cap[l] * (size_t)rstride * 8; }
+    /* device -> host, then the device copy is freed.  Page-locked host memory when it can be had (the copies then run at the
+     * link's rate), pageable otherwise.  false + nothing changed on failure. */
+    bool spill(cudaStream_t s)
+    {
+        if (spilled || !allocated()) return spilled;
+        hpinned = getenv("FLINT_B200_SPILL_PAGEABLE") == nullptr;
+        bool ok = true;
+        for (int pass = 0; pass < 2; ++pass) {             /* second pass: pageable, if page-locked memory ran out */
+            ok = true;
+            for (int l = 0; l < nlev && ok; ++l) {
+                hbase[l] = (double*)host_alloc(level_bytes(l));
+                ok = hbase[l] != nullptr;
+                if (ok && l >= 1) { hslot[l] = (int*)host_alloc((size_t)N * 4); ok = hslot[l] != nullptr; }
+            }
+            if (ok) { hdcount = (int*)host_alloc((size_t)N * 4); ok = hdcount != nullptr; }
+            if (ok || !hpinned) break;
+            release_host(); hpinned = false;
+        }
+        if (!ok) { release_host(); return false; }
+        for (int l = 0; l < nlev && ok; ++l) {
+            ok = cudaMemcpyAsync(hbase[l], base[l], level_bytes(l), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            if (ok && l >= 1) ok = cudaMemcpyAsync(hslot[l], slot[l], (size_t)N * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        }
+        ok = ok && cudaMemcpyAsync(hdcount, dcount, (size_t)N * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(hzflag, dzflag, 8, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); release_host(); return false; }
+        release_device();
+        spilled = true;
+        return true;
+    }
+    /* host -> device (the host copy stays: an Interpolate with SaveInterpCoeffs leaves the part spilled) */
+    bool restore(cudaStream_t s)
+    {
+        if (!spilled) return allocated();
+        bool ok = true;
+        for (int l = 0; l < nlev && ok; ++l) {
+            ok = cudaMalloc(&base[l], level_bytes(l)) == cudaSuccess;
+            if (ok && l >= 1) ok = cudaMalloc(&slot[l], (size_t)N * 4) == cudaSuccess;
+        }
+        ok = ok && cudaMalloc(&dcount, (size_t)N * 4) == cudaSuccess && cudaMalloc(&dzflag, 8) == cudaSuccess;
+        for (int l = 0; l < nlev && ok; ++l) {
+            ok = cudaMemcpyAsync(base[l], hbase[l], level_bytes(l), cudaMemcpyHostToDevice, s) == cudaSuccess;
+            if (ok && l >= 1) ok = cudaMemcpyAsync(slot[l], hslot[l], (size_t)N * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+        }
+        ok = ok && cudaMemcpyAsync(dcount, hdcount, (size_t)N * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(dzflag, hzflag, 8, cudaMemcpyHostToDevice, s) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); release_device(); return false; }
+        return true;
+    }
     void release()
     {
+        release_host();
         if (dzflag) cudaFree(dzflag);
         dzflag = nullptr;
         for (int l = 0; l < FLINT_DENSE_LEVELS; ++l) {
@@ -149,6 +234,9 @@ struct flint_erk {
     std::vector<cudaStream_t> shard_stream;
     std::vector<int> shard_device;
     long shard_N = 0, shard_chunk = 0;      /* the partition of the last sharded Integrate (Interpolate follows it) */
+    int shard_devices = 0;                  /* distinct device slots of that call: shard s ran on slot s % shard_devices, the parts
+                                               of a slot one after the other (flint_exec.dense_spill) */
+    bool shard_spill = false;               /* the parts' dense stores wait in host memory */
 };
 
 /* ------------------------------------------------------------------ misc */
@@ -375,7 +463,7 @@ struct DevBuf {
 struct ExecCtx {
     int device = 0; cudaStream_t stream = nullptr; bool host = true; bool async = false;
     long dense_cap = 0; int block = 0, blocks_per_sm = 0, event_mode = 0, plane_variant = 0, pipeline = 0, round_len = 0, dense_mode = 0;
-    int n_devices = 0; int devices[FLINT_MAX_DEVICES] = {0}; long shard_chunk = 0;
+    int n_devices = 0; int devices[FLINT_MAX_DEVICES] = {0}; long shard_chunk = 0; int dense_spill = 0;
 };
 
 /* Which columns of the caller's SoA host arrays (row pitch Ntot) a call works on: shard d of D in the block-cyclic deal of
@@ -625,6 +713,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
          * ever dropped.  cap0: flint_exec.dense_cap, else what a third of the free device memory holds, at most MaxSteps. ---- */
         if (dense) {
             DenseStore& D = me->dense;
+            if (D.spilled) D.release();                                /* a previous call's parts wait in host memory: gone with that call */
             const bool coef = ex.dense_mode == 1;
             const int rstride = dense_rstride(me, coef);
             long cap = ex.dense_cap > 0 ? ex.dense_cap : 0;
@@ -886,7 +975,7 @@ static ExecCtx make_exec(const flint_exec* x)
         e.device = x->device; e.stream = (cudaStream_t)x->stream; e.host = (x->mem == FLINT_MEM_HOST);
         e.async = x->async != 0 && !e.host; e.dense_cap = x->dense_cap; e.block = x->block_threads; e.blocks_per_sm = x->blocks_per_sm;
         e.event_mode = x->event_mode; e.plane_variant = x->plane_variant; e.pipeline = x->pipeline; e.round_len = x->round_len; e.dense_mode = x->dense_mode;
-        e.n_devices = x->n_devices; e.shard_chunk = x->shard_chunk > 0 ? x->shard_chunk : FLINT_SHARD_CHUNK;
+        e.n_devices = x->n_devices; e.shard_chunk = x->shard_chunk > 0 ? x->shard_chunk : FLINT_SHARD_CHUNK; e.dense_spill = x->dense_spill;
         for (int k = 0; k < FLINT_MAX_DEVICES; ++k) e.devices[k] = x->devices[k];
     }
     return e;
@@ -907,33 +996,55 @@ static void sync_options(flint_erk* dst, const flint_erk* src)
     dst->dense_allocated = src->dense_allocated;
 }
 
-/* The sub-handles and streams of a sharded call, created on first use and kept (staging buffers, workspaces, dense stores) */
-static int prepare_shards(flint_erk* me, const ExecCtx& ex)
+/* The sub-handles and streams of a sharded call, created on first use and kept (staging buffers, workspaces, dense stores).
+ * S shards over the D device slots of `devs`: shard s runs on devs[s % D]. */
+static int prepare_shards(flint_erk* me, const int* devs, int D, int S)
 {
-    const int D = ex.n_devices;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
     for (int k = 0; k < D; ++k) {
         /* a device may be listed more than once: its shards then share the GPU (two streams); the tests of a one-GPU box do that */
-        if (ex.devices[k] < 0 || ex.devices[k] >= ndev) return fail(FLINT_ERROR_PARAMS, "flint_exec.devices: no such CUDA device");
+        if (devs[k] < 0 || devs[k] >= ndev) return fail(FLINT_ERROR_PARAMS, "flint_exec.devices: no such CUDA device");
     }
-    bool same = (int)me->shard.size() == D;
-    for (int k = 0; same && k < D; ++k) same = me->shard_device[k] == ex.devices[k];
+    bool same = (int)me->shard.size() == S;
+    for (int k = 0; same && k < S; ++k) same = me->shard_device[k] == devs[k % D];
     if (!same) {
         for (size_t k = 0; k < me->shard.size(); ++k) {
             if (me->shard_stream[k]) { cudaSetDevice(me->shard_device[k]); cudaStreamDestroy(me->shard_stream[k]); }
             flint_erk_destroy(me->shard[k]);
         }
         me->shard.clear(); me->shard_stream.clear(); me->shard_device.clear();
-        for (int k = 0; k < D; ++k) {
+        for (int k = 0; k < S; ++k) {
             cudaStream_t st = nullptr;
-            if (!cuda_ok(cudaSetDevice(ex.devices[k]), "cudaSetDevice") ||
+            if (!cuda_ok(cudaSetDevice(devs[k % D]), "cudaSetDevice") ||
                 !cuda_ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return FLINT_ERROR;
-            me->shard.push_back(new flint_erk()); me->shard_stream.push_back(st); me->shard_device.push_back(ex.devices[k]);
+            me->shard.push_back(new flint_erk()); me->shard_stream.push_back(st); me->shard_device.push_back(devs[k % D]);
         }
     }
-    for (int k = 0; k < D; ++k) sync_options(me->shard[k], me);
+    for (int k = 0; k < S; ++k) sync_options(me->shard[k], me);
     return FLINT_SUCCESS;
+}
+
+/* flint_exec.dense_spill = 1: parts per device slot such that a part's dense store (first level at the depth an unspilled call
+ * would choose, at most 1024 steps; deeper levels only hold the trajectories that need them) stays within a third of the free
+ * memory of the emptiest device */
+static int auto_spill_parts(const flint_erk* me, long N, const int* devs, int D, const ExecCtx& ex)
+{
+    size_t fr_min = ~(size_t)0;
+    for (int k = 0; k < D; ++k) {
+        size_t fr = 0, tot = 0;
+        if (cudaSetDevice(devs[k]) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 1; }
+        if (fr < fr_min) fr_min = fr;
+    }
+    long cap = ex.dense_cap > 0 ? ex.dense_cap : 1024;
+    if (cap > me->max_steps) cap = me->max_steps;
+    cap = (cap + 127) / 128 * 128;
+    const double per_traj = (double)dense_rstride(me, ex.dense_mode == 1) * 8.0 * (double)cap;
+    const double need = per_traj * (double)((N + D - 1) / D);
+    if (const char* e = getenv("FLINT_B200_SPILL_BUDGET")) { const double b = atof(e); if (b > 0) fr_min = (size_t)b * 3; }   /* tests: bytes a part may use */
+    long parts = (long)(need / ((double)fr_min / 3.0)) + 1;
+    if (parts > 4096) parts = 4096;
+    return (int)parts;
 }
 
 extern "C" int flint_erk_integrate_batch(flint_erk_t* me, long N, double x0_scalar, const double* x0, const double* y0,
@@ -944,44 +1055,69 @@ extern "C" int flint_erk_integrate_batch(flint_erk_t* me, long N, double x0_scal
     if (!me) return FLINT_ERROR_PARAMS;
     if (!y0 || !xf || !yf) return me->status = fail(FLINT_ERROR_PARAMS, "y0, xf and yf are required");
     const ExecCtx ex = make_exec(exec);
-    if (ex.n_devices <= 1) {
+    if (ex.n_devices > FLINT_MAX_DEVICES) return me->status = fail(FLINT_ERROR_PARAMS, "flint_exec.n_devices > FLINT_MAX_DEVICES");
+    int devs[FLINT_MAX_DEVICES];
+    const int D = ex.n_devices >= 1 ? ex.n_devices : 1;
+    for (int k = 0; k < D; ++k) devs[k] = ex.n_devices >= 1 ? ex.devices[k] : ex.device;
+    /* ---- InterpOn with a dense output larger than device memory: parts whose stores wait in host memory (dense_spill) ---- */
+    int parts = 1;
+    if (ex.dense_spill != 0 && ex.host && me->inited && me->sys && me->interp_on && N > 0) {
+        parts = ex.dense_spill >= 2 ? ex.dense_spill : auto_spill_parts(me, N, devs, D, ex);
+        const long max_parts = (N / D + 127) / 128;          /* a part is at least 128 trajectories */
+        if (parts > max_parts) parts = (int)(max_parts < 1 ? 1 : max_parts);
+    }
+    const int S = D * parts;
+    if (S <= 1) {
         ExecCtx e1 = ex;
-        if (ex.n_devices == 1) e1.device = ex.devices[0];
-        me->shard_N = 0;
+        e1.device = devs[0];
+        me->shard_N = 0; me->shard_spill = false;
         return integrate_impl(me, N, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest, e1, false);
     }
     /* ---- the ensemble sharded over the devices of one box: chunks of shard_chunk trajectories dealt round-robin;
      * one host thread, one stream, one set of staging buffers per device; every trajectory is independent, so there is no
-     * exchange step and nothing to reduce -- results are copied to the caller's arrays at the trajectories' own offsets ---- */
+     * exchange step and nothing to reduce -- results are copied to the caller's arrays at the trajectories' own offsets.
+     * With dense_spill every device slot has `parts` shards and runs them one after the other ---- */
     if (!ex.host) return me->status = fail(FLINT_ERROR_PARAMS, "a sharded call takes host buffers (FLINT_MEM_HOST)");
-    if (ex.n_devices > FLINT_MAX_DEVICES) return me->status = fail(FLINT_ERROR_PARAMS, "flint_exec.n_devices > FLINT_MAX_DEVICES");
     if (!me->inited || !me->sys) return me->status = FLINT_ERROR_INIT_REQD;
     if (N <= 0) return me->status = FLINT_SUCCESS;
-    { const int rc = prepare_shards(me, ex); if (rc != FLINT_SUCCESS) return me->status = rc; }
-    const int D = ex.n_devices;
-    std::vector<int> rc(D, FLINT_SUCCESS);
-    std::vector<std::string> err(D);
+    { const int rc = prepare_shards(me, devs, D, S); if (rc != FLINT_SUCCESS) return me->status = rc; }
+    long chunk = ex.shard_chunk;
+    if (parts > 1 && chunk * S > N) { chunk = (N / S + 127) / 128 * 128; if (chunk < 128) chunk = 128; }   /* every part gets trajectories */
+    std::vector<int> rc(S, FLINT_SUCCESS);
+    std::vector<std::string> err(S);
     std::vector<std::thread> th;
-    for (int k = 0; k < D; ++k) {
-        th.emplace_back([&, k]() {
-            Shard sh; sh.Ntot = N; sh.D = D; sh.d = k; sh.chunk = ex.shard_chunk;
-            ExecCtx e1 = ex;
-            e1.device = ex.devices[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0; e1.pipeline = 1;
-            const long nk = shard_count(N, D, k, sh.chunk);
-            rc[k] = integrate_impl(me->shard[k], nk, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest,
-                                   e1, false, &sh);
-            if (rc[k] != FLINT_SUCCESS) err[k] = g_last_error;
+    const bool spill = parts > 1;
+    for (int d = 0; d < D; ++d) {
+        th.emplace_back([&, d]() {
+            for (int k = d; k < S; k += D) {
+                Shard sh; sh.Ntot = N; sh.D = S; sh.d = k; sh.chunk = chunk;
+                ExecCtx e1 = ex;
+                e1.device = devs[d]; e1.stream = me->shard_stream[k]; e1.n_devices = 0; e1.pipeline = 1;
+                const long nk = shard_count(N, S, k, sh.chunk);
+                flint_erk* sub = me->shard[k];
+                rc[k] = integrate_impl(sub, nk, x0_scalar, x0, y0, xf, yf, stepsz, io, counters, status, steps, events, stifftest,
+                                       e1, false, &sh);
+                if (rc[k] == FLINT_SUCCESS && spill && nk > 0) {
+                    /* the part's dense output to host memory; its staging buffers and workspace make room for the next part */
+                    if (!sub->dense.spill(e1.stream)) rc[k] = fail(FLINT_ERROR_MEMALLOC, "dense_spill: no host memory for a part's dense output");
+                    for (int q = 0; q < 2; ++q) { sub->stage_int[q].release(); sub->ws[q].release(); }
+                }
+                if (rc[k] != FLINT_SUCCESS) { err[k] = g_last_error; break; }
+            }
         });
     }
     for (auto& t : th) t.join();
     double ms = 0.0;
     int st = FLINT_SUCCESS;
-    for (int k = 0; k < D; ++k) {
-        if (me->shard[k]->last_kernel_ms > ms) ms = me->shard[k]->last_kernel_ms;
-        if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
+    for (int d = 0; d < D; ++d) {                              /* the call's device time: the slowest device slot (its parts add up) */
+        double md = 0.0;
+        for (int k = d; k < S; k += D) md += me->shard[k]->last_kernel_ms;
+        if (md > ms) ms = md;
     }
-    me->last_kernel_ms = ms; g_last_kernel_ms = ms;            /* the call's device time: the slowest shard */
-    me->shard_N = N; me->shard_chunk = ex.shard_chunk;
+    for (int k = 0; k < S; ++k)
+        if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
+    me->last_kernel_ms = ms; g_last_kernel_ms = ms;
+    me->shard_N = N; me->shard_chunk = chunk; me->shard_devices = D; me->shard_spill = spill;
     me->dense.release();                                       /* the dense output of this call lives in the shards */
     return me->status = st;
 }
@@ -1164,23 +1300,42 @@ static int interpolate_batch(flint_erk_t* me, const double* xarr, long G, double
          * caller's (host) Yarr at its trajectories' own offsets */
         if (!ex.host) return me->status = fail(FLINT_ERROR_PARAMS, "the dense output of a sharded Integrate is interpolated into host buffers");
         if (!me->interp_on) return me->status = FLINT_ERROR_INTP_OFF;
-        const int D = (int)me->shard.size();
-        std::vector<int> rc(D, FLINT_SUCCESS);
-        std::vector<std::string> err(D);
+        const int S = (int)me->shard.size(), D = me->shard_devices > 0 ? me->shard_devices : S;
+        const bool dealloc = has_save ? !save_coeffs : true;
+        std::vector<int> rc(S, FLINT_SUCCESS);
+        std::vector<std::string> err(S);
         std::vector<std::thread> th;
-        for (int k = 0; k < D; ++k)
-            th.emplace_back([&, k]() {
-                Shard sh; sh.Ntot = me->shard_N; sh.D = D; sh.d = k; sh.chunk = me->shard_chunk;
-                ExecCtx e1 = ex;
-                e1.device = me->shard_device[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0;
-                if (shard_count(sh.Ntot, D, k, sh.chunk) == 0) return;
-                rc[k] = interpolate_impl(me->shard[k], xarr, G, yarr, layout, status, has_save != 0, save_coeffs != 0, e1, false, &sh, per_traj);
-                if (rc[k] != FLINT_SUCCESS) err[k] = g_last_error;
+        for (int d = 0; d < D; ++d)
+            th.emplace_back([&, d]() {
+                for (int k = d; k < S; k += D) {
+                    Shard sh; sh.Ntot = me->shard_N; sh.D = S; sh.d = k; sh.chunk = me->shard_chunk;
+                    ExecCtx e1 = ex;
+                    e1.device = me->shard_device[k]; e1.stream = me->shard_stream[k]; e1.n_devices = 0;
+                    if (shard_count(sh.Ntot, S, k, sh.chunk) == 0) continue;
+                    flint_erk* sub = me->shard[k];
+                    const bool was_spilled = sub->dense.spilled;
+                    if (was_spilled) {                       /* the part's dense output back from host memory */
+                        if (!cuda_ok(cudaSetDevice(e1.device), "cudaSetDevice") || !sub->dense.restore(e1.stream)) {
+                            rc[k] = fail(FLINT_ERROR_MEMALLOC, "dense_spill: a part's dense output does not fit in device memory");
+                            err[k] = g_last_error;
+                            break;
+                        }
+                        sub->dense.spilled = false;          /* interpolate_impl sees an ordinary device store */
+                    }
+                    /* a spilled part keeps its host copy when the caller saves the coefficients: only the device copy goes */
+                    rc[k] = interpolate_impl(sub, xarr, G, yarr, layout, status, true, was_spilled ? true : !dealloc, e1, false, &sh, per_traj);
+                    if (was_spilled) {
+                        cudaSetDevice(e1.device);
+                        sub->dense.release_device();
+                        if (dealloc && rc[k] == FLINT_SUCCESS) { sub->dense.release(); sub->dense_allocated = false; }
+                        else sub->dense.spilled = true;
+                    }
+                    if (rc[k] != FLINT_SUCCESS) { err[k] = g_last_error; break; }
+                }
             });
         for (auto& t : th) t.join();
         int st = FLINT_SUCCESS;
-        for (int k = 0; k < D; ++k) if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
-        const bool dealloc = has_save ? !save_coeffs : true;
+        for (int k = 0; k < S; ++k) if (rc[k] != FLINT_SUCCESS && st == FLINT_SUCCESS) { st = rc[k]; g_last_error = err[k]; }
         if (dealloc && st == FLINT_SUCCESS) { me->dense_allocated = false; me->shard_N = 0; }
         return me->status = st;
     }

@@ -91,6 +91,7 @@ module FLINT_GPU
         integer(c_int) :: devices(FLINT_MAX_DEVICES) = 0
         integer(c_long) :: shard_chunk = 0
         integer(c_int) :: dense_mode = 0
+        integer(c_int) :: dense_spill = 0                     ! InterpOn: k >= 2 parts whose dense output waits in host memory, 1 = automatic
     end type
 
     interface

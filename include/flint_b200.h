@@ -174,6 +174,12 @@ typedef struct {
                            (the fused path); 1 = the coefficient record Bip(nI, 0:pstar) as the reference stores it
                            (src/ERKIntegrate.f90:555-566), built once at the end of Integrate: the cheaper choice when one
                            dense output is interpolated many times.  Results are identical. */
+    int dense_spill;    /* InterpOn, FLINT_MEM_HOST: the dense output of an ensemble that does not fit in device memory (the
+                           reference keeps Xint / Bip in host memory, src/ERKInit.f90:321-332).  k >= 2: the call runs as k parts per
+                           device, one after the other; after a part's Integrate its dense store is moved to host memory, and
+                           Interpolate brings the parts back one at a time (so Yarr needs device memory for one part only).
+                           1 = automatic: as many parts as keep a part's store within a third of the free device memory (one
+                           part = no spill).  0 = never.  Results are identical. */
 } flint_exec;
 
 /* ---- the partition of an ensemble over shards (devices of one call, or ranks of a multi-process job): trajectory index space

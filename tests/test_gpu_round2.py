@@ -382,3 +382,34 @@ def test_runtime_registered_systems(tmp_path, monkeypatch):
             assert g["nEvents"][i] == len(te), (g["nEvents"][i], len(te))
             assert np.allclose(g["EventStates"][0, :len(te), i], te, rtol=0, atol=1e-8)
             assert (g["EventStates"][3, :len(te), i] == 1.0).all()
+
+
+# ------------------------------------------------------------------------------------------------ dense output spilled to the host
+@pytest.mark.parametrize("kw", [dict(dense_spill=3), dict(dense_spill=2, devices=[0, 0]), dict(dense_spill=1, dense_mode=1),
+                                dict(dense_spill=4, dense_cap=128)])
+def test_dense_output_spilled_to_host_memory(kw, monkeypatch):
+    """an ensemble whose dense output does not fit in device memory runs as parts, one after the other; each
+    part's store waits in host memory between Integrate and Interpolate and comes back one part at a time (the reference keeps
+    Xint / Bip in host memory, src/ERKInit.f90:321-332).  Same results as the oracle, bit for bit: final states, events,
+    both Yarr layouts, a second Interpolate after SaveInterpCoeffs, storage gone after the last one.  dense_spill=1 picks the
+    number of parts from the memory budget (here a budget of 24 MB per part stands in for a full device)."""
+    if kw.get("dense_spill") == 1:
+        monkeypatch.setenv("FLINT_B200_SPILL_BUDGET", str(24 << 20))
+    case = K.cr3bp_case(F.ERK_VERNER98R, 1e-10, 0, norb=1.0, interp_on=True)
+    N = 1500
+    y0 = P.cr3bp_ensemble(N, start=11)
+    xarr = np.linspace(0.0, case.xf, 257)
+    xarr[-1] = case.xf
+    o = case.run_oracle(y0, xarr=xarr)
+    g = case.run_gpu(y0, shard_chunk=100, **kw)
+    K.compare_batch(g, o, case, "spilled dense %r" % kw)
+    erk = g["erk"]
+    for layout in (0, 1):
+        st, yarr, ist = erk.InterpolateBatch(xarr, N, SaveInterpCoeffs=True, layout=layout)
+        assert st == 0 and (ist == 0).all()
+        K.assert_bit_equal(yarr if layout == 0 else np.transpose(yarr, (2, 1, 0)), o["yarr"], "spilled Yarr layout %d %r" % (layout, kw))
+    st, yarr, ist = erk.InterpolateBatch(xarr[:40].copy(), N)          # the last one frees the storage
+    assert st == 0 and (ist == 0).all()
+    K.assert_bit_equal(yarr, o["yarr"][:, :40], "spilled Yarr, last call")
+    st, _, _ = erk.InterpolateBatch(xarr, N)
+    assert st == F.FLINT_ERROR_INTP_OFF
