@@ -518,6 +518,14 @@ static bool shard_copy(const Shard& sh, long N, long off, long cnt, void* dst, c
     return ok;
 }
 
+/* erk_dense_kernel writes a block's coefficient records with one bulk copy from shared memory (default) or thread by thread
+ * (FLINT_B200_DENSE_BULK=0; kept for comparison, profiles/r02_notes.md) */
+static int dense_bulk_default()
+{
+    static const int v = [] { const char* e = getenv("FLINT_B200_DENSE_BULK"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 /* what Init parsed, as the kernels' parameter block (everything that does not depend on one Integrate call) */
 static void fill_static_kargs(const flint_erk* me, KArgs& a)
 {
@@ -882,7 +890,7 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
             le = sweep(in, n_in, n_susp);
         }
         if (le == cudaSuccess && dense && me->dense.kind_coef) {   /* coefficient records from the logged steps (erk_kernel.cuh: erk_dense_kernel) */
-            c.dvo = c.dv; c.dense_eval = 0;
+            c.dvo = c.dv; c.dense_eval = 0; c.dense_bulk = dense_bulk_default();
             int* zf = c.zflag;
             c.zflag = (try_plane && ke->dense_plane) ? (int*)(ctr + 3) : nullptr;
             if (c.zflag) { le = flint::launch_dense(*ke, true, c, s); g_launches += 1; }
@@ -1246,7 +1254,7 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
             }
             flint::DenseView tv = T.view();
             for (int l = 1; l < D.nlev; ++l) tv.slot[l] = D.slot[l];
-            c.dense_eval = 0; c.dvo = tv;
+            c.dense_eval = 0; c.dvo = tv; c.dense_bulk = dense_bulk_default();
         }
         cudaError_t le = cudaSuccess;
         if (c.zflag) { le = flint::launch_dense(*ke, true, c, s); g_launches += 1; }

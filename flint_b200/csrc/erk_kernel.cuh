@@ -1155,7 +1155,7 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     if (p.dense_eval && p.istatus[t] != FLINT_SUCCESS) return;       /* this trajectory's grid failed the validation (:60-76) */
     const int ns = (int)(nacc - s0 < kDenseBlock ? nacc - s0 : kDenseBlock);
     const int tid = threadIdx.x;
-    extern __shared__ double dsm[];
+    extern __shared__ __align__(16) double dsm[];
     const int rs = (PS + 1) * p.nI, rsp = rs + (rs & 1);
     double* sB = dsm;                                       /* [128][rsp] */
     double* sX = dsm + kDenseBlock * rsp;                   /* [129] (+1 pad) */
@@ -1171,8 +1171,8 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
             if (p.dense_eval) {
                 sX[tid] = X; if (tid == ns - 1) sX[ns] = h;
                 for (int q = 0; q < rs; ++q) sB[tid * rsp + q] = rec[2 + q];
-            } else if (p.dvo.base[0] != p.dv.base[0]) {
-                double* __restrict__ o = p.dvo.rec(t, s0 + tid);
+            } else if (p.dense_bulk || p.dvo.base[0] != p.dv.base[0]) {
+                double* __restrict__ o = p.dense_bulk ? dsm + (long)tid * p.dvo.rstride : p.dvo.rec(t, s0 + tid);
                 o[0] = X; o[1] = h;
                 for (int q = 0; q < rs; ++q) o[2 + q] = rec[2 + q];
                 o[p.dvo.rstride - 1] = kDenseCoef;
@@ -1212,10 +1212,27 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
                             sB[tid * rsp + j * p.nI + ii] = v;
                         }
                 }
-            } else store_coef_record<METHOD, SYS>(p.dvo.rec(t, s0 + tid), p.dvo.rstride, p.nI, p.istates, X, X + h, B);
+            } else store_coef_record<METHOD, SYS>(p.dense_bulk ? dsm + (long)tid * p.dvo.rstride : p.dvo.rec(t, s0 + tid), p.dvo.rstride,
+                                                  p.nI, p.istates, X, X + h, B);
         }
     }
-    if (!p.dense_eval) return;
+    if (!p.dense_eval) {
+        if (p.dense_bulk) {
+        /* the block's records are contiguous in the store and were assembled in shared memory in the store's own layout: ONE bulk
+         * copy (TMA engine) writes them, instead of 29 scattered 16-byte stores per thread (ncu: lg_throttle 0.64 of 5.8 stall
+         * cycles per issue with two warps per sub-partition).  Every thread has read its log by now: in place is safe. */
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bytes = (unsigned)ns * (unsigned)p.dvo.rstride * 8u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(p.dvo.rec(t, s0)), "r"((unsigned)__cvta_generic_to_shared(dsm)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      /* shared memory may go once it has been read */
+        }
+        }
+        return;
+    }
     __syncthreads();
     const double hs = sign1(sX[1] - sX[0]);                 /* every step points in the direction of integration */
     const double* __restrict__ xg = p.ix + (p.ix_per_traj ? t * p.iG : 0L);

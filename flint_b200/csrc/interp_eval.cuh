@@ -91,23 +91,29 @@ __device__ __forceinline__ void block_step_ranges(const double* __restrict__ sX,
     }
     __syncthreads();
 }
+/* one warp evaluates the grid points [gA, gB) of the block's steps (gA >= sG[0], gB <= sG[ns]) */
 template <bool FMA, int PS, int NI, bool SOA>
-__device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, const long* __restrict__ sG,
-                                                 int ns, const double* __restrict__ xarr, long G, double* __restrict__ yout, long soa_n)
+__device__ __forceinline__ void eval_point_range(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, const long* __restrict__ sG,
+                                                 int ns, const double* __restrict__ xarr, long G, double* __restrict__ yout, long soa_n,
+                                                 long gA, long gB, int lane)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int per = (ns + nwarps - 1) / nwarps;
-    int i = warp * per;
-    const int iend = i + per < ns ? i + per : ns;
-    if (i >= iend) return;
-    long g = sG[i];
-    const long gend = sG[iend];
+    if (gA >= gB) return;
+    int i = 0;
+    {                                                                  /* the step that holds point gA: largest i with sG[i] <= gA */
+        int lo = 0, hi = ns - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sG[mid] <= gA) lo = mid; else hi = mid - 1; }
+        i = lo;
+    }
+    const int iend = ns;
+    long g = gA;
+    const long gend = gB;
     double xn = g + lane < gend ? xarr[g + lane] : 0.0;                /* the next batch's abscissae travel one iteration ahead */
     while (g < gend) {                                                 /* warp-uniform */
         while (sG[i + 1] <= g) ++i;                                    /* the step that holds point g (empty steps are skipped) */
         const long mid = sG[i + 1];                                    /* first point of step i + 1 */
         const long lim = i + 1 < iend ? sG[i + 2] : mid;               /* a batch ends with step i + 1 at the latest */
-        const long n = lim - g < 32 ? lim - g : 32;
+        long n = lim - g < 32 ? lim - g : 32;
+        n = gend - g < n ? gend - g : n;
         const long gl = g + lane;
         const double x = xn;
         { const long gq = g + n + lane; xn = gq < gend ? xarr[gq] : 0.0; }
@@ -153,6 +159,26 @@ __device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, 
         }
         g += n;
     }
+}
+
+/* warp `warp` of `nwarps` takes an equal share of the block's POINTS (steps hold 0 .. ~60 points each: equal shares of the steps
+ * leave the warps of a block unevenly loaded) */
+template <bool FMA, int PS, int NI, bool SOA>
+__device__ __forceinline__ void eval_steps_share(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, const long* __restrict__ sG,
+                                                 int ns, const double* __restrict__ xarr, long G, double* __restrict__ yout, long soa_n,
+                                                 int warp, int nwarps, int lane)
+{
+    const long g0 = sG[0], g1 = sG[ns];
+    const long per = (g1 - g0 + nwarps - 1) / nwarps;
+    long gA = g0 + warp * per, gB = gA + per;
+    if (gB > g1) gB = g1;
+    eval_point_range<FMA, PS, NI, SOA>(sB, rsp, sX, sG, ns, xarr, G, yout, soa_n, gA, gB, lane);
+}
+template <bool FMA, int PS, int NI, bool SOA>
+__device__ __forceinline__ void eval_block_steps(const double* __restrict__ sB, int rsp, const double* __restrict__ sX, const long* __restrict__ sG,
+                                                 int ns, const double* __restrict__ xarr, long G, double* __restrict__ yout, long soa_n)
+{
+    eval_steps_share<FMA, PS, NI, SOA>(sB, rsp, sX, sG, ns, xarr, G, yout, soa_n, threadIdx.x >> 5, blockDim.x >> 5, threadIdx.x & 31);
 }
 
 }  // namespace flint

@@ -17,6 +17,7 @@
  * (erk_kernel.cuh); it shares the step-major evaluation.
  */
 #include <cstdint>
+#include <cstdlib>
 #include "arith.cuh"
 #include "kargs.h"
 #include "interp_eval.cuh"
@@ -253,6 +254,201 @@ __global__ void __launch_bounds__(kStepsThreads, kStepsResident) interp_steps_ke
     eval_block_steps<FMA, PS, NI, SOA>(sR + 2, rstride, sX, sG, ns, xg, a.G, yo, a.N);
 }
 
+/* ======================================================================================================
+ * interp_tiles_kernel: the same evaluation as a PERSISTENT, warp-specialised pipeline.  interp_steps_kernel above is bound by
+ * the latency chain of each short-lived CTA (bulk copy -> step boundaries -> bisection -> evaluate: ncu long_scoreboard 2.6 and
+ * barrier 0.9 of ~10 stall cycles per issue, a third of the resident warps idle in a prologue at any time).  Here a CTA lives for
+ * the whole launch and walks tiles (trajectory, 64 consecutive steps) dealt round-robin; its warp 0 is the PRODUCER: for the tile
+ * kTileStages-1 ahead it arms an mbarrier and issues the bulk copy of the tile's records (cp.async.bulk, TMA engine), and for the
+ * tile whose copy has landed it reads the step boundaries from shared memory, counts each step's grid points (bisection with a
+ * uniform-grid guess) and publishes the tile on a second mbarrier.  The CONSUMER warps only ever wait on that barrier, evaluate
+ * their equal share of the tile's points (interp_eval.cuh) and hand the buffer back on a third.  Copies, range searches and
+ * evaluation of different tiles overlap; no consumer ever waits for HBM.
+ * ====================================================================================================== */
+#ifndef FLINT_TILE_STEPS
+#define FLINT_TILE_STEPS 64
+#endif
+#ifndef FLINT_TILE_CONSUMERS
+#define FLINT_TILE_CONSUMERS 8
+#endif
+#ifndef FLINT_TILE_STAGES
+#define FLINT_TILE_STAGES 2
+#endif
+#ifndef FLINT_TILE_CTAS
+#define FLINT_TILE_CTAS 3
+#endif
+constexpr int kTileSteps = FLINT_TILE_STEPS, kTileConsumers = FLINT_TILE_CONSUMERS, kTileStages = FLINT_TILE_STAGES;
+constexpr int kTileThreads = 32 * (kTileConsumers + 1);
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+/* doubles per pipeline stage: records, step boundaries, point ranges, tile header (16-byte multiples) */
+__host__ __device__ constexpr int tile_stage_doubles(int rstride) { return kTileSteps * rstride + 2 * (kTileSteps + 2) + 4; }
+
+template <bool FMA, int PS, int NI, bool SOA>
+__global__ void __launch_bounds__(kTileThreads, FLINT_TILE_CTAS) interp_tiles_kernel(InterpArgs a, long gy)
+{
+    const int rstride = a.dv.rstride;
+    const int stage_d = tile_stage_doubles(rstride);
+    extern __shared__ __align__(128) double tsm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (long)kTileStages * stage_d);   /* tx[S], ready[S], empty[S] */
+    uint64_t* bar_tx = bars; uint64_t* bar_ready = bars + kTileStages; uint64_t* bar_empty = bars + 2 * kTileStages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTileStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar_tx + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar_ready + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar_empty + s)), "r"(kTileConsumers));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long n_items = a.N * gy;
+    auto stage_rec = [&](int s) -> double* { return tsm + (long)s * stage_d; };
+    auto stage_x = [&](int s) -> double* { return stage_rec(s) + kTileSteps * rstride; };
+    auto stage_g = [&](int s) -> long* { return reinterpret_cast<long*>(stage_x(s) + kTileSteps + 2); };
+    auto stage_hdr = [&](int s) -> long* { return stage_g(s) + kTileSteps + 2; };          /* [0] trajectory, [1] ns (0: the end), [2] first step */
+
+    if (warp == 0) {
+        /* ------------------------------ producer ------------------------------ */
+        long item = blockIdx.x;                       /* next candidate tile */
+        long k_issue = 0, k_done = 0;                 /* tiles whose copy was issued / that were published */
+        long q_t[kTileStages], q_s0[kTileStages]; int q_ns[kTileStages]; long q_acc[kTileStages];
+        bool more = true;
+        while (more || k_done < k_issue) {
+            /* (1) publish the oldest tile in flight -- BEFORE the producer may block on a buffer below, so that the consumers
+             * always find their next tile ready: boundaries from the records in shared memory, ranges of grid points */
+            if (k_done < k_issue && (k_issue - k_done >= kTileStages - 1 || !more)) {
+                const int s = (int)(k_done % kTileStages);
+                mbar_wait(bar_tx + s, (unsigned)((k_done / kTileStages) & 1));
+                const long t = q_t[s], s0 = q_s0[s], acc = q_acc[s];
+                const int ns = q_ns[s];
+                const double* sR = stage_rec(s);
+                double* sX = stage_x(s);
+                long* sG = stage_g(s);
+                const double hs = sign1(sR[1] - sR[0]);            /* records are (X0, X1, ...): every step points in the direction of integration */
+                const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+                for (int i = lane; i <= ns; i += 32) {
+                    const double X = i < ns ? sR[(long)i * rstride] : sR[(long)(ns - 1) * rstride + 1];
+                    sX[i] = X;
+                    long g;
+                    if (i == 0) g = s0 == 0 ? 0 : grid_count_upto(xg, a.G, hs, X);
+                    else if (i == ns && s0 + ns == acc) g = a.G;
+                    else g = grid_count_upto(xg, a.G, hs, X);
+                    sG[i] = g;
+                }
+                if (lane == 0) { long* h = stage_hdr(s); h[0] = t; h[1] = ns; h[2] = s0; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready + s);          /* release: the consumers acquire with their wait */
+                ++k_done;
+            }
+            /* (2) the next tile's copy, as soon as its buffer is free (the tile kTileStages before it consumed) */
+            if (more && k_issue - k_done < kTileStages) {
+                long t = -1, s0 = 0, acc = 0;
+                for (; item < n_items; item += gridDim.x) {            /* skip tiles beyond a trajectory's last step / failed grids */
+                    t = item / gy; s0 = (item - t * gy) * kTileSteps;
+                    acc = a.dcount[t];
+                    if (s0 < acc && a.status[t] == FLINT_SUCCESS) break;
+                    t = -1;
+                }
+                if (t < 0) { more = false; continue; }
+                item += gridDim.x;
+                const int s = (int)(k_issue % kTileStages);
+                const int ns = (int)(acc - s0 < kTileSteps ? acc - s0 : kTileSteps);
+                if (k_issue >= kTileStages) mbar_wait(bar_empty + s, (unsigned)((k_issue / kTileStages - 1) & 1));
+                if (lane == 0) {
+                    const unsigned bytes = (unsigned)ns * (unsigned)rstride * 8u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_tx + s)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(stage_rec(s))), "l"(a.dv.rec(t, s0)), "r"(bytes), "r"(smem_u32(bar_tx + s)) : "memory");
+                }
+                q_t[s] = t; q_s0[s] = s0; q_ns[s] = ns; q_acc[s] = acc;
+                ++k_issue;
+            }
+        }
+        /* the end: one more "tile" with ns = 0 */
+        {
+            const int s = (int)(k_done % kTileStages);
+            if (k_done >= kTileStages) mbar_wait(bar_empty + s, (unsigned)((k_done / kTileStages - 1) & 1));
+            if (lane == 0) { stage_hdr(s)[1] = 0; mbar_arrive(bar_ready + s); }
+        }
+    } else {
+        /* ------------------------------ consumers ------------------------------ */
+        const int cw = warp - 1;
+        for (long k = 0;; ++k) {
+            const int s = (int)(k % kTileStages);
+            mbar_wait(bar_ready + s, (unsigned)((k / kTileStages) & 1));
+            const long* h = stage_hdr(s);
+            const int ns = (int)h[1];
+            if (ns == 0) break;
+            mbar_wait(bar_tx + s, (unsigned)((k / kTileStages) & 1));     /* complete long ago (the producer read the records): this thread's own view of the copy */
+            const long t = h[0];
+            const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+            double* yo = SOA ? a.yarr + t : a.yarr + t * a.G * NI;
+            eval_steps_share<FMA, PS, NI, SOA>(stage_rec(s) + 2, rstride, stage_x(s), stage_g(s), ns, xg, a.G, yo, a.N, cw, kTileConsumers, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + s);
+        }
+    }
+}
+
+template <bool FMA, int PS, int NI>
+static cudaError_t launch_tiles_one(const InterpArgs& a, int sm_count, cudaStream_t s)
+{
+    const long cap = a.dv.capacity();
+    const long gy = (cap + kTileSteps - 1) / kTileSteps;
+    if (gy < 1) return cudaErrorInvalidConfiguration;
+    const int smem = (kTileStages * tile_stage_doubles(a.dv.rstride) + 3 * kTileStages) * 8;
+    const void* k = a.layout == 0 ? (const void*)interp_tiles_kernel<FMA, PS, NI, false> : (const void*)interp_tiles_kernel<FMA, PS, NI, true>;
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    int bps = 0;
+    { const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTileThreads, (size_t)smem); if (e != cudaSuccess) return e; }
+    if (bps < 1) return cudaErrorInvalidConfiguration;
+    long grid = (long)sm_count * bps;
+    if (grid > a.N * gy) grid = a.N * gy;
+    InterpArgs b = a;
+    long gyv = gy;
+    void* args[2] = {&b, &gyv};
+    return cudaLaunchKernel(k, dim3((unsigned)grid), dim3(kTileThreads), args, (size_t)smem, s);
+}
+template <bool FMA, int PS>
+static cudaError_t launch_tiles_ni(const InterpArgs& a, int sm_count, cudaStream_t s)
+{
+    switch (a.nI) {
+    case 1: return launch_tiles_one<FMA, PS, 1>(a, sm_count, s);
+    case 2: return launch_tiles_one<FMA, PS, 2>(a, sm_count, s);
+    case 3: return launch_tiles_one<FMA, PS, 3>(a, sm_count, s);
+    case 4: return launch_tiles_one<FMA, PS, 4>(a, sm_count, s);
+    case 5: return launch_tiles_one<FMA, PS, 5>(a, sm_count, s);
+    case 6: return launch_tiles_one<FMA, PS, 6>(a, sm_count, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+template <bool FMA>
+static cudaError_t launch_tiles_ps(const InterpArgs& a, int sm_count, cudaStream_t s)
+{
+    switch (a.pstar) {
+    case 4: return launch_tiles_ni<FMA, 4>(a, sm_count, s);
+    case 5: return launch_tiles_ni<FMA, 5>(a, sm_count, s);
+    case 7: return launch_tiles_ni<FMA, 7>(a, sm_count, s);
+    case 8: return launch_tiles_ni<FMA, 8>(a, sm_count, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 template <bool FMA, int PS, int NI>
 static cudaError_t launch_steps_one(const InterpArgs& a, cudaStream_t s)
 {
@@ -345,7 +541,10 @@ cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, 
             return a.fma ? launch_soa_ps<true>(a, grid1, s) : launch_soa_ps<false>(a, grid1, s);
         }
     }
-    return a.fma ? launch_steps_ps<true>(a, s) : launch_steps_ps<false>(a, s);
+    /* FLINT_B200_INTERP_KERNEL=steps: the one-tile-per-CTA kernel (kept for comparison; profiles/r02_notes.md) */
+    static const bool use_steps = [] { const char* e = getenv("FLINT_B200_INTERP_KERNEL"); return !(e && e[0] == 't'); }();
+    if (use_steps) return a.fma ? launch_steps_ps<true>(a, s) : launch_steps_ps<false>(a, s);
+    return a.fma ? launch_tiles_ps<true>(a, sm_count, s) : launch_tiles_ps<false>(a, sm_count, s);
 }
 
 }  // namespace flint

@@ -121,6 +121,7 @@ struct KArgs {
      * the grid ix[G] (per trajectory: ix[N][G]) is evaluated into iy[N][G][nI] straight from the coefficients in registers */
     DenseView dvo;
     int dense_eval, ix_per_traj; long iG; const double* ix; double* iy; const int* istatus;
+    int dense_bulk;                              /* dense_eval == 0: the block's records are staged in shared memory and written by one bulk copy */
     /* trajectory state block + work lists (erk_kernel.cuh) */
     double* sd; int* si; long scap;              /* [fields][scap] */
     const int* list_in; const unsigned long long* n_in;   /* trajectories of this pass (NULL: all of [0, N)) */

@@ -127,7 +127,8 @@ cudaError_t launch_dense(const KernelEntry& e, bool plane, const KArgs& a, cudaS
     long gy = (cap + kDenseBlock - 1) / kDenseBlock;
     if (gy < 1) gy = 1;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const int smem = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : 0;
+    /* fused evaluation: coefficients + ranges; otherwise the block's records, staged for one bulk store (erk_dense_kernel) */
+    const int smem = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : (a.dense_bulk ? kDenseBlock * a.dvo.rstride * 8 : 0);
     if (smem > 48 * 1024) {
         const cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (er != cudaSuccess) return er;
