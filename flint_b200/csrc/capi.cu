@@ -552,7 +552,10 @@ static int dense_rstride(const flint_erk* me, bool coef)
     int r = me->events_on ? 3 * n + 3 : 2 * n + 2;
     if (coef && me->nI * (me->pstar + 1) + 2 > r) r = me->nI * (me->pstar + 1) + 2;
     r += 1;
-    return r + (r & 1);
+    r += r & 1;
+    if (coef) r += (r % 4 == 0) ? 2 : 0;      /* an odd number of 16-byte units: records of different steps start in different banks of
+                                                 shared memory when a tile of them arrives as one bulk copy (interp_items_kernel) */
+    return r;
 }
 
 static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double* x0, const double* y0, double* xf,
@@ -1218,8 +1221,9 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D.device);
     if (D.kind_coef) {                                       /* coefficient records: the evaluation kernels (interp_kernel.cu) */
-        if (!cuda_ok(flint::launch_interp(a, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
-        g_launches += 2;
+        int nl = 0;
+        if (!cuda_ok(flint::launch_interp(a, up, down, sms, s, &nl), "interp launch")) return me->status = FLINT_ERROR;
+        g_launches += nl;
     } else {
         /* step logs: erk_dense_kernel rebuilds every step's coefficients in registers and (layout 0) evaluates the grid from
          * there -- the fused path; for [nI][G][N] it writes them to a temporary coefficient store first */
@@ -1244,7 +1248,7 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
             c.ix = a.xarr; c.iy = a.yarr; c.iG = G; c.ix_per_traj = a.per_traj; c.istatus = a.status;
         } else {
             T.device = D.device; T.N = N; T.n = D.n; T.nI = D.nI; T.pstar = D.pstar; T.kind_coef = true; T.nlev = D.nlev;
-            T.rstride = D.nI * (D.pstar + 1) + 3; T.rstride += T.rstride & 1;
+            T.rstride = D.nI * (D.pstar + 1) + 3; T.rstride += T.rstride & 1; T.rstride += (T.rstride % 4 == 0) ? 2 : 0;
             for (int l = 0; l < D.nlev; ++l) {
                 T.cap[l] = D.cap[l]; T.rows[l] = D.rows[l];
                 if (cudaMalloc(&T.base[l], (size_t)T.rows[l] * (size_t)T.cap[l] * (size_t)T.rstride * 8) != cudaSuccess) {
@@ -1263,8 +1267,9 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
         if (layout != 0) {
             flint::InterpArgs b = a;
             b.dv = c.dvo;
-            if (!cuda_ok(flint::launch_interp(b, up, down, sms, s), "interp launch")) return me->status = FLINT_ERROR;
-            g_launches += 2;
+            int nl = 0;
+            if (!cuda_ok(flint::launch_interp(b, up, down, sms, s, &nl), "interp launch")) return me->status = FLINT_ERROR;
+            g_launches += nl;
             if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;   /* before the temporary store goes */
         }
     }

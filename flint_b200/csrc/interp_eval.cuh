@@ -64,6 +64,34 @@ __device__ __forceinline__ long grid_count_upto(const double* __restrict__ xarr,
     return lo;
 }
 
+/* the same count when it can be had from ONE round of loads: the three grid points around the uniform-grid guess, fetched
+ * together.  Split in two so that a caller can do other work (or start other searches) while the loads travel: grid_probe_issue
+ * computes the guess and issues the loads, grid_probe_result decides; ok = false: not decided, call grid_count_upto.
+ * xa = xarr[0], xb = xarr[G-1] (loaded once per caller). */
+struct GridProbe { double X, q0, q1, q2; long c; };
+__device__ __forceinline__ void grid_probe_issue(GridProbe& p, const double* __restrict__ xarr, long G, double X, double xa, double xb)
+{
+    const double fr = (X - xa) / (xb - xa);
+    long c = (fr >= 0.0 && fr <= 1.0) ? (long)(fr * (double)(G - 1)) : 0;      /* NaN and out-of-range guesses land on 0 */
+    c = c > G - 1 ? G - 1 : c;
+    const long cm = c > 0 ? c - 1 : 0, cp = c < G - 1 ? c + 1 : G - 1;
+    p.X = X; p.c = c;
+    p.q0 = xarr[cm]; p.q1 = xarr[c]; p.q2 = xarr[cp];
+}
+__device__ __forceinline__ long grid_probe_result(const GridProbe& p, long G, double hs, double xa, double xb, bool& ok)
+{
+    const bool first = before_dir(hs, p.X, xa), none = !before_dir(hs, p.X, xb);
+    const bool b0 = before_dir(hs, p.X, p.q0), b1 = before_dir(hs, p.X, p.q1), b2 = before_dir(hs, p.X, p.q2);
+    long res = 0;
+    bool done = false;
+    if (b1) { if (p.c == 0) { res = 0; done = true; } else if (!b0) { res = p.c; done = true; } }
+    else if (p.c < G - 1 && b2) { res = p.c + 1; done = true; }
+    if (none) { res = G; done = true; }
+    if (first) { res = 0; done = true; }
+    ok = done;
+    return res;
+}
+
 /* The CTA evaluates the grid points of its `ns` (<= kEvalSteps) consecutive steps of ONE trajectory.
  *   sB   [ns][rsp]   coefficients of step i at sB + i * rsp (16-byte aligned when NI is even), B[k][ii] k-major
  *   sX   [ns + 1]    sX[i] = start of step i, sX[ns] = end of the last one

@@ -288,6 +288,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity)       /* has the phase of that parity completed?  Does not block */
+{
+    unsigned ok = 0;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -399,6 +406,339 @@ __global__ void __launch_bounds__(kTileThreads, FLINT_TILE_CTAS) interp_tiles_ke
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + s);
         }
+    }
+}
+
+/* ======================================================================================================
+ * interp_items_kernel ([N][G][nI], nI even): the coefficients live in REGISTERS and the results leave as bulk stores.
+ *
+ * The kernels above put a warp's lanes on 32 consecutive grid points, so every lane re-reads its step's 54 coefficients from
+ * shared memory for every point (27 16-byte reads, two wavefronts each when the batch straddles two steps) and the warp's 48-byte
+ * results leave as three strided 16-byte stores (12 cache lines each): ~92 L1 wavefronts per 32 points beside ~57 cycles of fp64
+ * issue and ~100 cycles of HBM time per SM -- three co-bound pipes -- and each short-lived CTA starts with a chain of dependent
+ * loads (status, step count, boundaries, range search) that a third of the resident warps sit in at any time.
+ *
+ * Here the work item is (step, chunk of <= P consecutive grid points of that step) and a THREAD owns an item: it reads the
+ * step's coefficients from shared memory ONCE, keeps them in registers for its <= P points, and drops each result into its
+ * warp's staging buffer in shared memory at the point's place in Yarr.  The 32 items of a warp are consecutive in point order,
+ * so the buffer is one contiguous piece of Yarr: one lane sends it with a bulk store (cp.async.bulk shared -> global, TMA
+ * engine) while the warp already works on its next 32 items.  P is odd, so lanes on full chunks of one step hit distinct banks
+ * with their 16-byte stores (P * 12 words = 20 mod 32 for P = 7), and the records sit in shared memory with a padded stride
+ * (29 x 16 bytes for Verner98R, 6 states) for the same reason: one bulk copy per record, all completing on one mbarrier.
+ *
+ * The kernel is persistent (one CTA per SM, trajectories dealt round-robin, a trajectory's tiles of 64 consecutive steps in
+ * sequence) and warp-specialised.  Warp 0 is the HELPER: kItemsStages tiles ahead it issues the bulk copy of a tile's records
+ * (cp.async.bulk, completion on an mbarrier), and for the oldest tile that has landed it finds the first grid point of every
+ * step -- 65 boundaries on 32 lanes, three searches side by side, one round of loads each for a near-uniform grid
+ * (grid_count_try) -- and the first item of every step (warp scan), and publishes the tile on a second mbarrier.  The eleven
+ * CONSUMER warps deal the 32-item rounds of the tile stream among themselves round-robin and never wait for anything but the
+ * "tile planned" barrier.
+ * ====================================================================================================== */
+#ifndef FLINT_ITEMS_P
+#define FLINT_ITEMS_P 5
+#endif
+#ifndef FLINT_ITEMS_CONSUMERS
+#define FLINT_ITEMS_CONSUMERS 11
+#endif
+#ifndef FLINT_ITEMS_STAGES
+#define FLINT_ITEMS_STAGES 4
+#endif
+constexpr int kItemsP = FLINT_ITEMS_P, kItemsConsumers = FLINT_ITEMS_CONSUMERS, kItemsStages = FLINT_ITEMS_STAGES;
+constexpr int kItemsThreads = 32 * (kItemsConsumers + 1);
+#ifndef FLINT_ITEMS_STEPS
+#define FLINT_ITEMS_STEPS 64
+#endif
+constexpr int kItemsSteps = FLINT_ITEMS_STEPS;      /* steps per tile: 32 or 64 (divides the 128-step granularity of the capacity levels) */
+constexpr int kPlanRow = kItemsSteps + 4;           /* int2 per tile: [i] = (first grid point, first item) of step i, [ns] = (end, items);
+                                                       [65] = (trajectory, ns), [66] = (first step, steps of the trajectory) */
+/* record stride in shared memory: >= rstride and = 2 mod 4 doubles, i.e. an odd number of 16-byte units (the store's own stride
+ * is that already -- capi.cu: dense_rstride -- and a tile is ONE bulk copy; any other store is copied record by record) */
+__host__ __device__ constexpr int items_rsp(int rstride) { return rstride + ((2 - rstride % 4) + 4) % 4; }
+__host__ __device__ constexpr int items_stage_doubles(int rstride) { return kItemsSteps * items_rsp(rstride) + kPlanRow; }
+__host__ __device__ constexpr int items_smem_doubles(int rstride, int ni)
+{
+    return kItemsStages * items_stage_doubles(rstride) + 3 * kItemsStages /* barriers */ + (kItemsStages & 1) + kItemsConsumers * 32 * kItemsP * ni;
+}
+
+template <bool FMA, int PS, int NI>
+__global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpArgs a)
+{
+    static_assert(NI % 2 == 0, "16-byte results");
+    constexpr int P = kItemsP, S = kItemsStages;
+    const int rstride = a.dv.rstride, rsp = items_rsp(rstride);
+    const int stage_d = items_stage_doubles(rstride);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) double ism[];
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(ism + (long)S * stage_d);      /* records landed (transaction bytes) */
+    uint64_t* bar_ready = bar_full + S;                                             /* tile planned (helper) */
+    uint64_t* bar_empty = bar_ready + S;                                            /* tile consumed (every consumer warp) */
+    double* sYall = reinterpret_cast<double*>(bar_empty + S + (S & 1));
+    auto stage_rec = [&](int s) -> double* { return ism + (long)s * stage_d; };
+    auto stage_row = [&](int s) -> int2* { return reinterpret_cast<int2*>(stage_rec(s) + kItemsSteps * rsp); };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar_full + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar_ready + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar_empty + s)), "r"(kItemsConsumers));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        /* ------------------------------ helper: bulk copies ahead, ranges and items of what has landed ------------------------------ */
+        constexpr int NB = kItemsSteps / 32;                            /* boundaries per lane (+ the last one, on every lane) */
+        long k_issue = 0, k_probe = 0, k_done = 0;                      /* tiles whose copy was issued / whose searches are in flight / published */
+        /* the trajectories of this CTA, 32 at a time: step counts (0: none / failed grid) one batch ahead of their use */
+        long tb = blockIdx.x;                                           /* first trajectory of the current batch */
+        int q = 32;                                                     /* next lane of the batch; 32: load a batch */
+        long my_acc = 0;
+        long cur_t = -1, cur_acc = 0, cur_s0 = 0;                       /* trajectory being dealt, next step to issue */
+        bool more = true;
+        double xa = 0.0, xb = 0.0; long x_t = -2;                       /* grid ends of the trajectory whose grid is loaded */
+        GridProbe pr[NB + 1];
+        /* The helper never blocks on a barrier: a tile that has not landed, or a buffer that is not free yet, is looked at again in
+         * the next turn of the loop, so that publishing what is ready never waits for either */
+        while (more || k_done < k_issue) {
+            bool did = false;
+            /* (1) publish the tile whose searches were started in the previous iteration: their loads travelled meanwhile */
+            if (k_done < k_probe) {
+                did = true;
+                const int s = (int)(k_done % S);
+                int2* row = stage_row(s);
+                const long t = row[kItemsSteps + 1].x;
+                const int ns = row[kItemsSteps + 1].y;
+                const long s0 = row[kItemsSteps + 2].x, acc = row[kItemsSteps + 2].y;
+                const double* sR = stage_rec(s);
+                const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+                const double hs = sign1(sR[1] - sR[0]);                  /* records are (X0, X1, ...): every step points in the direction of integration */
+                int g[NB + 1];
+#pragma unroll
+                for (int u = 0; u <= NB; ++u) {
+                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
+                    bool ok;
+                    const long r = grid_probe_result(pr[u], a.G, hs, xa, xb, ok);
+                    if (i > ns) g[u] = 0;
+                    else if (i == 0 && s0 == 0) g[u] = 0;
+                    else if (i == ns && s0 + ns == acc) g[u] = (int)a.G;
+                    else g[u] = (int)(ok ? r : grid_count_upto(xg, a.G, hs, pr[u].X));
+                }
+                int base = 0;                                             /* items of the steps before this group of 32 */
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    int nxt = __shfl_down_sync(0xffffffffu, g[u], 1);
+                    const int g_up = __shfl_sync(0xffffffffu, g[u + 1 < NB ? u + 1 : u], 0);
+                    if (lane == 31) nxt = u + 1 < NB ? g_up : g[NB];
+                    const int i = lane + 32 * u;
+                    const int c = i < ns ? (nxt - g[u] + P - 1) / P : 0;   /* items of step i */
+                    int inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+                    if (i <= ns) row[i] = make_int2(g[u], base + inc - c);
+                    base += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0 && ns == kItemsSteps) row[kItemsSteps] = make_int2(g[NB], base);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready + s);                 /* release: the consumers acquire with their wait */
+                ++k_done;
+            }
+            /* (2) start the searches of the next tile that has landed (its copy was issued at least two tiles ago) */
+            if (k_probe < k_issue && k_probe == k_done && mbar_test(bar_full + (int)(k_probe % S), (unsigned)((k_probe / S) & 1))) {
+                did = true;
+                const int s = (int)(k_probe % S);
+                const int2* row = stage_row(s);
+                const long t = row[kItemsSteps + 1].x;
+                const int ns = row[kItemsSteps + 1].y;
+                const double* sR = stage_rec(s);
+                const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+                const long xt = a.per_traj ? t : -1;
+                if (xt != x_t) { xa = xg[0]; xb = xg[a.G - 1]; x_t = xt; }
+#pragma unroll
+                for (int u = 0; u <= NB; ++u) {
+                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
+                    const double X = i < ns ? sR[(long)i * rsp] : (i == ns ? sR[(long)(ns - 1) * rsp + 1] : xa);
+                    grid_probe_issue(pr[u], xg, a.G, X, xa, xb);
+                }
+                ++k_probe;
+            }
+            /* (3) the next tile's copy, as soon as its buffer is free (the tile kItemsStages before it consumed) */
+            if (more && k_issue - k_done < S && (k_issue < S || mbar_test(bar_empty + (int)(k_issue % S), (unsigned)((k_issue / S - 1) & 1)))) {
+                did = true;
+                while (cur_t < 0 || cur_s0 >= cur_acc) {                   /* next trajectory with steps left */
+                    if (q == 32) {
+                        if (tb >= a.N) { more = false; break; }
+                        const long tq = tb + (long)lane * gridDim.x;
+                        my_acc = (tq < a.N && a.status[tq] == FLINT_SUCCESS) ? a.dcount[tq] : 0;
+                        q = 0;
+                    }
+                    cur_t = tb + (long)q * gridDim.x;
+                    cur_acc = __shfl_sync(0xffffffffu, my_acc, q);
+                    cur_s0 = 0;
+                    if (++q == 32) tb += 32L * gridDim.x;
+                    if (cur_t >= a.N) { more = false; cur_t = -1; break; }
+                }
+                if (!more) continue;
+                const long t = cur_t, s0 = cur_s0, acc = cur_acc;
+                const int ns = (int)(acc - s0 < kItemsSteps ? acc - s0 : kItemsSteps);
+                cur_s0 += kItemsSteps;
+                const int s = (int)(k_issue % S);
+                const double* __restrict__ src = a.dv.rec(t, s0);
+                double* dst = stage_rec(s);
+                if (lane == 0) {
+                    int2* row = stage_row(s);
+                    row[kItemsSteps + 1] = make_int2((int)t, ns);
+                    row[kItemsSteps + 2] = make_int2((int)s0, (int)acc);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                 ::"r"(smem_u32(bar_full + s)), "r"((unsigned)ns * (unsigned)rstride * 8u) : "memory");
+                }
+                __syncwarp();
+                if (rsp == rstride) {                                      /* ONE bulk copy */
+                    if (lane == 0)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(smem_u32(dst)), "l"(src), "r"((unsigned)ns * (unsigned)rstride * 8u), "r"(smem_u32(bar_full + s)) : "memory");
+                } else {
+                    for (int i = lane; i < ns; i += 32)                    /* one bulk copy per record, into its padded slot */
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(smem_u32(dst + (long)i * rsp)), "l"(src + (long)i * rstride), "r"((unsigned)rstride * 8u), "r"(smem_u32(bar_full + s)) : "memory");
+                }
+                ++k_issue;
+            }
+            if (!did) __nanosleep(100);
+        }
+        /* the end: one more "tile" without steps */
+        {
+            const int s = (int)(k_done % S);
+            if (k_done >= S) mbar_wait(bar_empty + s, (unsigned)((k_done / S - 1) & 1));
+            if (lane == 0) { stage_row(s)[kItemsSteps + 1] = make_int2(-1, 0); mbar_arrive(bar_ready + s); }
+        }
+        return;
+    }
+    /* ------------------------------ consumers ------------------------------ */
+    const int cw = warp - 1;
+    double* sY = sYall + (long)cw * 32 * P * NI;                       /* this warp's piece of Yarr */
+    bool pending = false;                                              /* a bulk store of sY may still be reading it */
+    int roff = 0;                                                      /* rounds dealt so far, mod the number of consumers */
+    for (long k = 0;; ++k) {
+        const int s = (int)(k % S);
+        mbar_wait(bar_ready + s, (unsigned)((k / S) & 1));
+        const int2* row = stage_row(s);
+        const int ns = row[kItemsSteps + 1].y;
+        if (ns == 0) break;
+        mbar_wait(bar_full + s, (unsigned)((k / S) & 1));              /* complete long ago (the helper read the records): this thread's own view of the copy */
+        const double* sR = stage_rec(s);
+        const long t = row[kItemsSteps + 1].x;
+        const int T = row[ns].y;
+        const int R = (T + 31) >> 5;
+        const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+        double* __restrict__ yo = a.yarr + t * a.G * NI;
+        int r = cw - roff; if (r < 0) r += kItemsConsumers;
+        for (; r < R; r += kItemsConsumers) {
+            const int kk = r * 32 + lane < T ? r * 32 + lane : T - 1;
+            const bool valid = r * 32 + lane < T;
+            int i;
+            {                                                          /* the step of item kk: largest i with first_item[i] <= kk */
+                int lo = 0, hi = ns - 1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row[mid].y <= kk) lo = mid; else hi = mid - 1; }
+                i = lo;
+            }
+            const int2 e0 = row[i];
+            const int ge = row[i + 1].x;
+            int ga = e0.x + (kk - e0.y) * P;
+            int len = ge - ga < P ? ge - ga : P;
+            if (!valid) { ga = ge; len = 0; }
+            const int wbase = __shfl_sync(0xffffffffu, ga, 0);
+            const int wend = __shfl_sync(0xffffffffu, ga + len, 31);   /* items are consecutive in point order; invalid lanes sit at the end */
+            double xs[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) xs[j] = j < len ? xg[ga + j] : 0.0;
+            double2 b[(PS + 1) * (NI / 2)];
+            const double* rec = sR + (long)i * rsp;
+            {
+                const double2* __restrict__ B2 = reinterpret_cast<const double2*>(rec + 2);
+#pragma unroll
+                for (int q = 0; q < (PS + 1) * (NI / 2); ++q) b[q] = B2[q];
+            }
+            const double X0 = rec[0], h = rec[1] - X0;
+            if (pending) {                                             /* the previous piece has left shared memory */
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            double2* __restrict__ o = reinterpret_cast<double2*>(sY + (long)(ga - wbase) * NI);
+            /* FMA arithmetic (not bound by the fp64 pipe): every lane evaluates P points, those beyond its chunk on x = 0 and
+             * unused -- no branch separates the points and the division chain of the next one overlaps the sums of this one.
+             * Strict arithmetic (bound by the fp64 pipe): a point is evaluated only by the lanes that have it */
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                if (FMA || j < len) {
+                    const double theta = (xs[j] - X0) / h;             /* InterpY, :124-140 */
+                    double tk[PS + 1], y[NI];
+                    theta_powers<PS>(theta, tk);
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) y[q] = 0.0;
+#pragma unroll
+                    for (int kq = 0; kq <= PS; ++kq)
+#pragma unroll
+                        for (int q = 0; q < NI / 2; ++q) {
+                            y[2 * q] = madd<FMA>(b[kq * (NI / 2) + q].x, tk[kq], y[2 * q]);
+                            y[2 * q + 1] = madd<FMA>(b[kq * (NI / 2) + q].y, tk[kq], y[2 * q + 1]);
+                        }
+                    if (j < len) {
+#pragma unroll
+                        for (int q = 0; q < NI / 2; ++q) o[j * (NI / 2) + q] = make_double2(y[2 * q], y[2 * q + 1]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the generic-proxy writes above, visible to the bulk store */
+            __syncwarp();
+            if (lane == 0 && wend > wbase) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(yo + (long)wbase * NI), "r"(smem_u32(sY)), "r"((unsigned)((wend - wbase) * NI * 8)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            pending = true;
+        }
+        roff = (roff + R) % kItemsConsumers;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + s);
+    }
+    if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* shared memory outlives its readers */
+}
+
+template <bool FMA, int PS, int NI>
+static cudaError_t launch_items_one(const InterpArgs& a, int sm_count, cudaStream_t s, bool* served)
+{
+    if constexpr (NI % 2 != 0) return cudaSuccess;
+    else {
+        if (a.G < 1 || a.N > 0x7fffffffL || a.G > 0x7fffffffL / 8 || a.dv.capacity() > 0x7fffffffL) return cudaSuccess;
+        const int smem = items_smem_doubles(a.dv.rstride, NI) * 8;
+        if (smem > 227 * 1024) return cudaSuccess;                     /* records too large for the pipeline: the step-major kernel serves */
+        cudaError_t e = cudaFuncSetAttribute(interp_items_kernel<FMA, PS, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        const long grid = a.N < sm_count ? a.N : sm_count;
+        interp_items_kernel<FMA, PS, NI><<<(unsigned)grid, kItemsThreads, smem, s>>>(a);
+        *served = true;
+        return cudaGetLastError();
+    }
+}
+template <bool FMA, int PS>
+static cudaError_t launch_items_ni(const InterpArgs& a, int sm_count, cudaStream_t s, bool* served)
+{
+    switch (a.nI) {
+    case 2: return launch_items_one<FMA, PS, 2>(a, sm_count, s, served);
+    case 4: return launch_items_one<FMA, PS, 4>(a, sm_count, s, served);
+    case 6: return launch_items_one<FMA, PS, 6>(a, sm_count, s, served);
+    default: return cudaSuccess;
+    }
+}
+template <bool FMA>
+static cudaError_t launch_items_ps(const InterpArgs& a, int sm_count, cudaStream_t s, bool* served)
+{
+    switch (a.pstar) {
+    case 4: return launch_items_ni<FMA, 4>(a, sm_count, s, served);
+    case 5: return launch_items_ni<FMA, 5>(a, sm_count, s, served);
+    case 7: return launch_items_ni<FMA, 7>(a, sm_count, s, served);
+    case 8: return launch_items_ni<FMA, 8>(a, sm_count, s, served);
+    default: return cudaSuccess;
     }
 }
 
@@ -522,9 +862,10 @@ static cudaError_t launch_soa_ps(const InterpArgs& a, dim3 grid, cudaStream_t s)
     }
 }
 
-cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, cudaStream_t s)
+cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, cudaStream_t s, int* launches)
 {
     InterpArgs a = a0;
+    if (launches) *launches = 2;                                       /* validation + one evaluation kernel */
     const cudaError_t ev = launch_interp_validate(a, up, down, s);
     if (ev != cudaSuccess) return ev;
     /* structure-of-arrays output, enough trajectories to fill the device with threads, one shared grid */
@@ -541,8 +882,17 @@ cudaError_t launch_interp(const InterpArgs& a0, int up, int down, int sm_count, 
             return a.fma ? launch_soa_ps<true>(a, grid1, s) : launch_soa_ps<false>(a, grid1, s);
         }
     }
-    /* FLINT_B200_INTERP_KERNEL=steps: the one-tile-per-CTA kernel (kept for comparison; profiles/r02_notes.md) */
-    static const bool use_steps = [] { const char* e = getenv("FLINT_B200_INTERP_KERNEL"); return !(e && e[0] == 't'); }();
+    /* FLINT_B200_INTERP_KERNEL = items | steps | tiles picks one kernel for comparison (profiles/r02_notes.md); by default the
+     * thread-per-item kernel takes every [N][G][nI] call it can serve (nI even, 16-byte aligned Yarr), the step-major one the rest */
+    const int which = [] { const char* e = getenv("FLINT_B200_INTERP_KERNEL"); return !e ? 0 : e[0] == 'i' ? 1 : e[0] == 's' ? 2 : e[0] == 't' ? 3 : 0; }();
+    const bool items_ok = a.layout == 0 && a.nI % 2 == 0 && (reinterpret_cast<uintptr_t>(a.yarr) & 15) == 0;
+    if (items_ok && which <= 1) {
+        bool served = false;
+        const cudaError_t e = a.fma ? launch_items_ps<true>(a, sm_count, s, &served) : launch_items_ps<false>(a, sm_count, s, &served);
+        if (e != cudaSuccess) return e;
+        if (served) return cudaSuccess;
+    }
+    const bool use_steps = which != 3;
     if (use_steps) return a.fma ? launch_steps_ps<true>(a, s) : launch_steps_ps<false>(a, s);
     return a.fma ? launch_tiles_ps<true>(a, sm_count, s) : launch_tiles_ps<false>(a, sm_count, s);
 }

@@ -156,7 +156,7 @@ struct InterpArgs {
     long chunk; int nchunks;         /* filled by launch_interp */
 };
 #ifndef __CUDACC_RTC__             /* ---- host side: launchers and the table of integrate kernels ---- */
-cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t);
+cudaError_t launch_interp(const InterpArgs&, int grid_up, int grid_down, int sm_count, cudaStream_t, int* launches = nullptr);   /* *launches = kernels launched */
 /* per-trajectory validation of the grid (src/ERKInterp.f90:60-76) against any kind of records */
 cudaError_t launch_interp_validate(const InterpArgs&, int grid_up, int grid_down, cudaStream_t);
 /* slot[list[j]] = j for j < n: rows of a new level of the dense store (registry.cu) */

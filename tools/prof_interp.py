@@ -15,7 +15,7 @@ r = erk.IntegrateBatch(0.0, y0, xf, StepSz=0.0, dense_cap=1024, dense_mode=mode,
 print("integrate ms", r["kernel_ms"])
 xarr = torch.linspace(0.0, xf, G, dtype=torch.float64).cuda(); xarr[-1] = xf
 yarr = torch.empty((N, G, 6) if layout == 0 else (6, G, N), dtype=torch.float64, device="cuda")
-for _ in range(2):
+for _ in range(4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); st, _, ist = erk.InterpolateBatch(xarr, N, SaveInterpCoeffs=True, layout=layout, out=yarr); e1.record(); torch.cuda.synchronize()
     print("interpolate ms", e0.elapsed_time(e1), "ok", float((ist == 0).float().mean()))
