@@ -67,11 +67,11 @@ __device__ __forceinline__ long grid_count_upto(const double* __restrict__ xarr,
 /* the same count when it can be had from ONE round of loads: the three grid points around the uniform-grid guess, fetched
  * together.  Split in two so that a caller can do other work (or start other searches) while the loads travel: grid_probe_issue
  * computes the guess and issues the loads, grid_probe_result decides; ok = false: not decided, call grid_count_upto.
- * xa = xarr[0], xb = xarr[G-1] (loaded once per caller). */
+ * xa = xarr[0], xb = xarr[G-1], inv_span = 1 / (xb - xa) (once per caller). */
 struct GridProbe { double X, q0, q1, q2; long c; };
-__device__ __forceinline__ void grid_probe_issue(GridProbe& p, const double* __restrict__ xarr, long G, double X, double xa, double xb)
+__device__ __forceinline__ void grid_probe_issue(GridProbe& p, const double* __restrict__ xarr, long G, double X, double xa, double inv_span)
 {
-    const double fr = (X - xa) / (xb - xa);
+    const double fr = (X - xa) * inv_span;                                    /* inv_span = 1 / (xb - xa): a guess only, verified by the loads */
     long c = (fr >= 0.0 && fr <= 1.0) ? (long)(fr * (double)(G - 1)) : 0;      /* NaN and out-of-range guesses land on 0 */
     c = c > G - 1 ? G - 1 : c;
     const long cm = c > 0 ? c - 1 : 0, cp = c < G - 1 ? c + 1 : G - 1;

@@ -8,8 +8,9 @@
  * contiguous within a capacity level.  Every grid point gets the reference's step (forward cursor of :85-103) and
  * Y = sum_k B(:,k) * theta**k exactly as InterpY (:124-140; powers in __powidf2 order, arith.cuh).
  *
- *   interp_steps_kernel   [N][G][nI] (each trajectory a Fortran Yarr(nI,G)); also [nI][G][N] for small ensembles and grown
- *                         stores.  A CTA = 128 consecutive steps of one trajectory: their records arrive as ONE bulk copy
+ *   interp_items_kernel   [N][G][nI] with an even nI (each trajectory a Fortran Yarr(nI,G)): persistent, warp-specialised; a
+ *                         thread keeps one step's coefficients in registers for <= 3 grid points, results leave as bulk stores.
+ *   interp_steps_kernel   [N][G][nI] with an odd nI; also [nI][G][N] for small ensembles and grown stores.  A CTA = 128 consecutive steps of one trajectory: their records arrive as ONE bulk copy
  *                         (cp.async.bulk, completion on an mbarrier) and are evaluated step-major (interp_eval.cuh).
  *   interp_kernel_soa     [nI][G][N] with >= 4096 trajectories: one THREAD per trajectory, lanes on consecutive trajectories
  *                         -> coalesced stores, coefficients in registers.
@@ -419,29 +420,38 @@ __global__ void __launch_bounds__(kTileThreads, FLINT_TILE_CTAS) interp_tiles_ke
  * loads (status, step count, boundaries, range search) that a third of the resident warps sit in at any time.
  *
  * Here the work item is (step, chunk of <= P consecutive grid points of that step) and a THREAD owns an item: it reads the
- * step's coefficients from shared memory ONCE, keeps them in registers for its <= P points, and drops each result into its
- * warp's staging buffer in shared memory at the point's place in Yarr.  The 32 items of a warp are consecutive in point order,
- * so the buffer is one contiguous piece of Yarr: one lane sends it with a bulk store (cp.async.bulk shared -> global, TMA
- * engine) while the warp already works on its next 32 items.  P is odd, so lanes on full chunks of one step hit distinct banks
- * with their 16-byte stores (P * 12 words = 20 mod 32 for P = 7), and the records sit in shared memory with a padded stride
- * (29 x 16 bytes for Verner98R, 6 states) for the same reason: one bulk copy per record, all completing on one mbarrier.
+ * step's coefficients from shared memory ONCE, keeps them in registers for its <= P points (the point-independent first term
+ * of the sum, 0 + B(:,0) * theta**0, is formed once per item), and drops each result into its warp's staging buffer in shared
+ * memory at the point's place in Yarr.  The 32 items of a warp are consecutive in point order, so the buffer is one
+ * contiguous piece of Yarr: one lane sends it with a bulk store (cp.async.bulk shared -> global, TMA engine) while the warp
+ * already works on its next 32 items.  P is odd, so lanes on full chunks of one step hit distinct banks with their 16-byte
+ * stores (P * 12 words = 4 mod 32 for P = 3), and the store's record stride is an odd number of 16-byte units (capi.cu:
+ * dense_rstride; 29 for Verner98R with 6 states) so that lanes on different steps read their coefficients from different
+ * banks although a tile of records arrives as ONE bulk copy.
  *
  * The kernel is persistent (one CTA per SM, trajectories dealt round-robin, a trajectory's tiles of 64 consecutive steps in
- * sequence) and warp-specialised.  Warp 0 is the HELPER: kItemsStages tiles ahead it issues the bulk copy of a tile's records
- * (cp.async.bulk, completion on an mbarrier), and for the oldest tile that has landed it finds the first grid point of every
- * step -- 65 boundaries on 32 lanes, three searches side by side, one round of loads each for a near-uniform grid
- * (grid_count_try) -- and the first item of every step (warp scan), and publishes the tile on a second mbarrier.  The eleven
- * CONSUMER warps deal the 32-item rounds of the tile stream among themselves round-robin and never wait for anything but the
- * "tile planned" barrier.
+ * sequence) and warp-specialised.  Warp 0 is the HELPER: up to kItemsStages tiles ahead it issues the bulk copy of a tile's
+ * records (completion on an mbarrier); for a tile that has landed it reads the step boundaries from shared memory and starts
+ * the search for the first grid point of every step -- 65 boundaries on 32 lanes, three searches side by side, one round of
+ * loads each for a near-uniform grid (grid_probe_issue); the searches of two tiles are in flight, and the older one is finished
+ * (grid_probe_result, warp scan for the first item of every step) and published on a second mbarrier.  The helper never blocks
+ * on a barrier.  The eleven CONSUMER warps deal the 32-item rounds of the tile stream among themselves round-robin and wait
+ * for nothing but the "tile planned" barrier.
+ *
+ * Measured (2^15 orbits x 10^4 points x 6 states, Verner98R, profiles/r02_notes.md): 5.78 -> 4.68 ms strict, 5.68 -> 4.40 ms
+ * FMA against interp_steps_kernel.  Measured and dropped: a separate planning kernel (0.73 ms: 8 useful bytes per 64 fetched),
+ * one bulk copy per record into padded slots (TMA issue-bound), the next round's search and x loads one round ahead (spills,
+ * 6.3 ms), theta from a reciprocal of h kept per item (5.2 ms: the range check and fall-back per point cost more than the five
+ * DFMA they save), 32-step tiles (helper-bound), P = 5 / 7 and 10 consumers.
  * ====================================================================================================== */
 #ifndef FLINT_ITEMS_P
-#define FLINT_ITEMS_P 5
+#define FLINT_ITEMS_P 3
 #endif
 #ifndef FLINT_ITEMS_CONSUMERS
 #define FLINT_ITEMS_CONSUMERS 11
 #endif
 #ifndef FLINT_ITEMS_STAGES
-#define FLINT_ITEMS_STAGES 4
+#define FLINT_ITEMS_STAGES 5
 #endif
 constexpr int kItemsP = FLINT_ITEMS_P, kItemsConsumers = FLINT_ITEMS_CONSUMERS, kItemsStages = FLINT_ITEMS_STAGES;
 constexpr int kItemsThreads = 32 * (kItemsConsumers + 1);
@@ -495,14 +505,37 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
         long my_acc = 0;
         long cur_t = -1, cur_acc = 0, cur_s0 = 0;                       /* trajectory being dealt, next step to issue */
         bool more = true;
-        double xa = 0.0, xb = 0.0; long x_t = -2;                       /* grid ends of the trajectory whose grid is loaded */
-        GridProbe pr[NB + 1];
+        double xa = 0.0, xb = 0.0, inv_span = 0.0; long x_t = -2;       /* grid ends of the trajectory whose grid is loaded */
+        /* the searches of up to TWO tiles are in flight (prA: the older), so a tile's loads have a whole turn of the loop to arrive */
+        GridProbe prA[NB + 1], prB[NB + 1];
+        int n_fly = 0;
         /* The helper never blocks on a barrier: a tile that has not landed, or a buffer that is not free yet, is looked at again in
          * the next turn of the loop, so that publishing what is ready never waits for either */
         while (more || k_done < k_issue) {
-            bool did = false;
-            /* (1) publish the tile whose searches were started in the previous iteration: their loads travelled meanwhile */
-            if (k_done < k_probe) {
+            bool did = false, probed = false;
+            /* (1) start the searches of the next tile that has landed */
+            if (n_fly < 2 && k_probe < k_issue && mbar_test(bar_full + (int)(k_probe % S), (unsigned)((k_probe / S) & 1))) {
+                did = true; probed = true;
+                const int s = (int)(k_probe % S);
+                const int2* row = stage_row(s);
+                const long t = row[kItemsSteps + 1].x;
+                const int ns = row[kItemsSteps + 1].y;
+                const double* sR = stage_rec(s);
+                const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
+                const long xt = a.per_traj ? t : -1;
+                if (xt != x_t) { xa = xg[0]; xb = xg[a.G - 1]; inv_span = 1.0 / (xb - xa); x_t = xt; }
+#pragma unroll
+                for (int u = 0; u <= NB; ++u) {
+                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
+                    const double X = i < ns ? sR[(long)i * rsp] : (i == ns ? sR[(long)(ns - 1) * rsp + 1] : xa);
+                    if (n_fly == 0) grid_probe_issue(prA[u], xg, a.G, X, xa, inv_span);
+                    else grid_probe_issue(prB[u], xg, a.G, X, xa, inv_span);
+                }
+                ++n_fly;
+                ++k_probe;
+            }
+            /* (2) publish the oldest tile in flight, once a second one is behind it (or nothing could be started this turn) */
+            if (n_fly == 2 || (n_fly == 1 && !probed)) {
                 did = true;
                 const int s = (int)(k_done % S);
                 int2* row = stage_row(s);
@@ -512,16 +545,18 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                 const double* sR = stage_rec(s);
                 const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
                 const double hs = sign1(sR[1] - sR[0]);                  /* records are (X0, X1, ...): every step points in the direction of integration */
+                double ta = xa, tb2 = xb;                                 /* a per-trajectory grid: the ends of THIS tile's grid (the newer tile may have another) */
+                if (a.per_traj && x_t != t) { ta = xg[0]; tb2 = xg[a.G - 1]; }
                 int g[NB + 1];
 #pragma unroll
                 for (int u = 0; u <= NB; ++u) {
                     const int i = u < NB ? lane + 32 * u : kItemsSteps;
                     bool ok;
-                    const long r = grid_probe_result(pr[u], a.G, hs, xa, xb, ok);
+                    const long r = grid_probe_result(prA[u], a.G, hs, ta, tb2, ok);
                     if (i > ns) g[u] = 0;
                     else if (i == 0 && s0 == 0) g[u] = 0;
                     else if (i == ns && s0 + ns == acc) g[u] = (int)a.G;
-                    else g[u] = (int)(ok ? r : grid_count_upto(xg, a.G, hs, pr[u].X));
+                    else g[u] = (int)(ok ? r : grid_count_upto(xg, a.G, hs, prA[u].X));
                 }
                 int base = 0;                                             /* items of the steps before this group of 32 */
 #pragma unroll
@@ -541,25 +576,9 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready + s);                 /* release: the consumers acquire with their wait */
                 ++k_done;
-            }
-            /* (2) start the searches of the next tile that has landed (its copy was issued at least two tiles ago) */
-            if (k_probe < k_issue && k_probe == k_done && mbar_test(bar_full + (int)(k_probe % S), (unsigned)((k_probe / S) & 1))) {
-                did = true;
-                const int s = (int)(k_probe % S);
-                const int2* row = stage_row(s);
-                const long t = row[kItemsSteps + 1].x;
-                const int ns = row[kItemsSteps + 1].y;
-                const double* sR = stage_rec(s);
-                const double* __restrict__ xg = a.xarr + (a.per_traj ? t * a.G : 0L);
-                const long xt = a.per_traj ? t : -1;
-                if (xt != x_t) { xa = xg[0]; xb = xg[a.G - 1]; x_t = xt; }
+                --n_fly;
 #pragma unroll
-                for (int u = 0; u <= NB; ++u) {
-                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
-                    const double X = i < ns ? sR[(long)i * rsp] : (i == ns ? sR[(long)(ns - 1) * rsp + 1] : xa);
-                    grid_probe_issue(pr[u], xg, a.G, X, xa, xb);
-                }
-                ++k_probe;
+                for (int u = 0; u <= NB; ++u) prA[u] = prB[u];
             }
             /* (3) the next tile's copy, as soon as its buffer is free (the tile kItemsStages before it consumed) */
             if (more && k_issue - k_done < S && (k_issue < S || mbar_test(bar_empty + (int)(k_issue % S), (unsigned)((k_issue / S - 1) & 1)))) {
@@ -659,6 +678,9 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                 for (int q = 0; q < (PS + 1) * (NI / 2); ++q) b[q] = B2[q];
             }
             const double X0 = rec[0], h = rec[1] - X0;
+            /* the sum's first term, 0 + B(:,0) * theta**0, does not depend on the point: once per item (same operations, same bits) */
+#pragma unroll
+            for (int q = 0; q < NI / 2; ++q) { b[q].x = madd<FMA>(b[q].x, 1.0, 0.0); b[q].y = madd<FMA>(b[q].y, 1.0, 0.0); }
             if (pending) {                                             /* the previous piece has left shared memory */
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
@@ -674,9 +696,9 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                     double tk[PS + 1], y[NI];
                     theta_powers<PS>(theta, tk);
 #pragma unroll
-                    for (int q = 0; q < NI; ++q) y[q] = 0.0;
+                    for (int q = 0; q < NI / 2; ++q) { y[2 * q] = b[q].x; y[2 * q + 1] = b[q].y; }
 #pragma unroll
-                    for (int kq = 0; kq <= PS; ++kq)
+                    for (int kq = 1; kq <= PS; ++kq)
 #pragma unroll
                         for (int q = 0; q < NI / 2; ++q) {
                             y[2 * q] = madd<FMA>(b[kq * (NI / 2) + q].x, tk[kq], y[2 * q]);

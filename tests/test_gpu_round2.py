@@ -299,6 +299,30 @@ def test_config4_shape_fused_and_separate(arith):
         K.assert_bit_equal(np.transpose(yarr, (2, 1, 0)), o["yarr"], "config 4 Yarr [nI][G][N], dense_mode %d" % dense_mode)
 
 
+@pytest.mark.parametrize("method,arith", [(F.ERK_VERNER98R, 0), (F.ERK_VERNER98R, 1), (F.ERK_DOP853, 0), (F.ERK_DOP54, 0), (F.ERK_VERNER65E, 1)])
+def test_interpolation_kernels_agree_bit_for_bit(method, arith, monkeypatch):
+    """The [N][G][nI] evaluation kernels -- thread-per-item with bulk stores (the default for an even nI), step-major CTAs and the
+    persistent tile pipeline (FLINT_B200_INTERP_KERNEL) -- give the oracle's Yarr bit for bit: a non-uniform grid that leaves
+    steps without points and packs hundreds of points into others (every item length 1..P, rounds that straddle tiles), grid
+    points that coincide with the ends of the span, nI = 6 and the subset nI = 4 (InterpStates), a store that grew a level."""
+    for istates in (None, [1, 2, 4, 5]):
+        case = K.cr3bp_case(method, 1e-10, arith, interp_on=True, interp_states=istates, eventset=F.FLINT_EVSET_NONE)
+        N, G = 200, 4001
+        y0 = P.cr3bp_ensemble(N, start=512)
+        u = np.linspace(0.0, 1.0, G)
+        xarr = case.xf * (0.5 * u + 0.5 * u ** 7)                          # dense early, sparse late
+        xarr[-1] = case.xf
+        o = case.run_oracle(y0, xarr=xarr)
+        g = case.run_gpu(y0, dense_mode=1, dense_cap=256)
+        for kern in ("items", "steps", "tiles"):
+            monkeypatch.setenv("FLINT_B200_INTERP_KERNEL", kern)
+            st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True)
+            ok = g["status"] == 0                                           # a trajectory that stopped early has no dense output up to Xf
+            assert ok.sum() > N // 2 and (ist[ok] == 0).all()
+            K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr, kernel %s, method %d, nI %d" % (kern, method, yarr.shape[2]))
+        monkeypatch.delenv("FLINT_B200_INTERP_KERNEL")
+
+
 def test_per_trajectory_grids():
     """flint_erk_interpolate_batch_grids: one grid per trajectory (ragged spans: every trajectory has its own Xf), a backward
     ensemble, and a row that leaves its trajectory's span (FLINT_ERROR_INTP_ARRAY for that trajectory only)."""
