@@ -1243,6 +1243,57 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
         c.zflag = me->dense_plane_ok ? D.dzflag : nullptr;
         DenseStore T;                                        /* temporary coefficient records ([nI][G][N] output) */
         struct Guard { DenseStore& t; ~Guard() { t.release(); } } guard{T};
+        /* [N][G][nI] from step logs, two ways.  STAGED (default where the thread-per-item evaluation kernel serves, i.e. an even
+         * nI): the ensemble goes through a small temporary coefficient store in parts of a few thousand trajectories -- the dense
+         * kernel turns a part's logs into coefficient records, the evaluation kernel reads them back (mostly from L2) and writes
+         * Yarr -- so both phases run their best kernel and the store the caller keeps is still the 4x smaller one of step logs.
+         * FUSED (FLINT_B200_DENSE_EVAL=fused, odd nI, or no memory for the temporary): one kernel, the coefficients go from
+         * registers through shared memory straight into the evaluation, Bip never exists in device memory. */
+        bool staged = false;
+        if (layout == 0 && D.nI % 2 == 0 && (reinterpret_cast<uintptr_t>(a.yarr) & 15) == 0) {
+            const char* e = getenv("FLINT_B200_DENSE_EVAL");
+            staged = !(e && e[0] == 'f');
+        }
+        if (staged) {
+            T.device = D.device; T.n = D.n; T.nI = D.nI; T.pstar = D.pstar; T.kind_coef = true; T.nlev = D.nlev;
+            T.rstride = D.nI * (D.pstar + 1) + 3; T.rstride += T.rstride & 1; T.rstride += (T.rstride % 4 == 0) ? 2 : 0;
+            const size_t per_traj = (size_t)D.cap[0] * (size_t)T.rstride * 8;
+            long part = (long)(((size_t)1 << 31) / per_traj);                 /* ~2 GB of records per part */
+            { const char* e = getenv("FLINT_B200_DENSE_PART"); if (e && atol(e) > 0) part = atol(e); }
+            if (part < 256) part = 256;
+            if (part > N) part = N;
+            T.N = part;
+            bool ok = true;
+            for (int l = 0; l < D.nlev && ok; ++l) {
+                T.cap[l] = D.cap[l]; T.rows[l] = l == 0 ? part : D.rows[l];
+                ok = cudaMalloc(&T.base[l], (size_t)T.rows[l] * (size_t)T.cap[l] * (size_t)T.rstride * 8) == cudaSuccess;
+            }
+            if (!ok) { cudaGetLastError(); T.release(); T = DenseStore(); staged = false; }   /* no room: the fused kernel needs none */
+        }
+        if (staged) {
+            c.dense_eval = 0; c.dense_bulk = dense_bulk_default();
+            for (long t0 = 0; t0 < N; t0 += T.N) {
+                const long nc = N - t0 < T.N ? N - t0 : T.N;
+                /* the part's view of the logs and of the temporary store: level 0 is indexed by trajectory, deeper levels through
+                 * the slot tables (rows of the whole ensemble) */
+                flint::DenseView lv = a.dv, tv = T.view();
+                lv.base[0] += (size_t)t0 * (size_t)D.cap[0] * (size_t)D.rstride;
+                for (int l = 1; l < D.nlev; ++l) { lv.slot[l] = D.slot[l] + t0; tv.slot[l] = D.slot[l] + t0; }
+                c.N = nc; c.dv = lv; c.dvo = tv; c.dense_count = D.dcount + t0;
+                cudaError_t le = cudaSuccess;
+                if (c.zflag) { le = flint::launch_dense(*ke, true, c, s); g_launches += 1; }
+                if (le == cudaSuccess) { le = flint::launch_dense(*ke, false, c, s); g_launches += 1; }
+                if (!cuda_ok(le, "dense kernel launch")) return me->status = FLINT_ERROR;
+                flint::InterpArgs b = a;
+                b.N = nc; b.dv = tv; b.dcount = D.dcount + t0; b.status = a.status + t0;
+                b.yarr = a.yarr + (size_t)t0 * (size_t)G * (size_t)D.nI;
+                if (a.per_traj) b.xarr = a.xarr + (size_t)t0 * (size_t)G;
+                int nl = 0;
+                if (!cuda_ok(flint::launch_interp(b, up, down, sms, s, &nl), "interp launch")) return me->status = FLINT_ERROR;
+                g_launches += nl;
+            }
+            if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;   /* before the temporary store goes */
+        } else {
         if (layout == 0) {
             c.dense_eval = 1; c.dvo = c.dv;
             c.ix = a.xarr; c.iy = a.yarr; c.iG = G; c.ix_per_traj = a.per_traj; c.istatus = a.status;
@@ -1271,6 +1322,7 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
             if (!cuda_ok(flint::launch_interp(b, up, down, sms, s, &nl), "interp launch")) return me->status = FLINT_ERROR;
             g_launches += nl;
             if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;   /* before the temporary store goes */
+        }
         }
     }
     std::vector<int> hst;

@@ -323,6 +323,31 @@ def test_interpolation_kernels_agree_bit_for_bit(method, arith, monkeypatch):
         monkeypatch.delenv("FLINT_B200_INTERP_KERNEL")
 
 
+@pytest.mark.parametrize("method,cap", [(F.ERK_VERNER98R, 1024), (F.ERK_DOP54, 128), (F.ERK_DOP853, 256)])
+def test_staged_and_fused_evaluation_from_step_logs(method, cap, monkeypatch):
+    """Interpolate [N][G][nI] from a store of step logs (dense_mode 0): STAGED through a temporary coefficient store in parts of
+    trajectories (default; parts of 256 here, the last one ragged, a store that grew levels for DOP54) and FUSED in one kernel
+    (FLINT_B200_DENSE_EVAL=fused) both equal the oracle bit for bit, with a shared grid and with one grid per trajectory."""
+    case = K.cr3bp_case(method, 1e-9, 0, interp_on=True, eventset=F.FLINT_EVSET_NONE)
+    N, G = 600, 1501
+    y0 = P.cr3bp_ensemble(N, start=8192)
+    xarr = np.linspace(0.0, case.xf, G); xarr[-1] = case.xf
+    o = case.run_oracle(y0, xarr=xarr)
+    g = case.run_gpu(y0, dense_mode=0, dense_cap=cap)
+    ok = g["status"] == 0
+    assert ok.sum() > N // 2
+    grids = np.repeat(xarr[None, :], N, axis=0)
+    monkeypatch.setenv("FLINT_B200_DENSE_PART", "256")
+    for how in ("staged", "fused"):
+        monkeypatch.setenv("FLINT_B200_DENSE_EVAL", how)
+        st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True)
+        assert st == 0 and (ist[ok] == 0).all()
+        K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr from step logs, %s, method %d" % (how, method))
+        st, yarr, ist = g["erk"].InterpolateBatch(grids, N, SaveInterpCoeffs=True)
+        assert st == 0 and (ist[ok] == 0).all()
+        K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr from step logs, per-trajectory grids, %s, method %d" % (how, method))
+
+
 def test_per_trajectory_grids():
     """flint_erk_interpolate_batch_grids: one grid per trajectory (ragged spans: every trajectory has its own Xf), a backward
     ensemble, and a row that leaves its trajectory's span (FLINT_ERROR_INTP_ARRAY for that trajectory only)."""
