@@ -1254,30 +1254,47 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
             const char* e = getenv("FLINT_B200_DENSE_EVAL");
             staged = !(e && e[0] == 'f');
         }
+        double* tb[FLINT_DENSE_LEVELS] = {nullptr};          /* the staged path's temporary records: stream-ordered allocations */
+        int trs = 0; long part = 0;
         if (staged) {
-            T.device = D.device; T.n = D.n; T.nI = D.nI; T.pstar = D.pstar; T.kind_coef = true; T.nlev = D.nlev;
-            T.rstride = D.nI * (D.pstar + 1) + 3; T.rstride += T.rstride & 1; T.rstride += (T.rstride % 4 == 0) ? 2 : 0;
-            const size_t per_traj = (size_t)D.cap[0] * (size_t)T.rstride * 8;
-            long part = (long)(((size_t)1 << 31) / per_traj);                 /* ~2 GB of records per part */
+            /* freed blocks stay in the device's pool between calls (the default hands them back to the driver at the next
+             * synchronisation, and mapping 2 GB again costs every call several milliseconds) */
+            static std::atomic<unsigned long long> pool_kept{0};
+            if (D.device >= 0 && D.device < 64 && !((pool_kept.load() >> D.device) & 1ull)) {
+                cudaMemPool_t pool = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&pool, D.device) == cudaSuccess) {
+                    unsigned long long keep = 3ull << 30;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+                cudaGetLastError();
+                pool_kept.fetch_or(1ull << D.device);
+            }
+            trs = D.nI * (D.pstar + 1) + 3; trs += trs & 1; trs += (trs % 4 == 0) ? 2 : 0;
+            const size_t per_traj = (size_t)D.cap[0] * (size_t)trs * 8;
+            part = (long)(((size_t)1 << 30) / per_traj);                      /* ~1 GB of records per part */
             { const char* e = getenv("FLINT_B200_DENSE_PART"); if (e && atol(e) > 0) part = atol(e); }
             if (part < 256) part = 256;
             if (part > N) part = N;
-            T.N = part;
             bool ok = true;
-            for (int l = 0; l < D.nlev && ok; ++l) {
-                T.cap[l] = D.cap[l]; T.rows[l] = l == 0 ? part : D.rows[l];
-                ok = cudaMalloc(&T.base[l], (size_t)T.rows[l] * (size_t)T.cap[l] * (size_t)T.rstride * 8) == cudaSuccess;
+            for (int l = 0; l < D.nlev && ok; ++l)
+                ok = cudaMallocAsync(&tb[l], (size_t)(l == 0 ? part : D.rows[l]) * (size_t)D.cap[l] * (size_t)trs * 8, s) == cudaSuccess;
+            if (!ok) {                                                        /* no room: the fused kernel needs none */
+                cudaGetLastError();
+                for (int l = 0; l < D.nlev; ++l) if (tb[l]) { cudaFreeAsync(tb[l], s); tb[l] = nullptr; }
+                staged = false;
             }
-            if (!ok) { cudaGetLastError(); T.release(); T = DenseStore(); staged = false; }   /* no room: the fused kernel needs none */
         }
         if (staged) {
+            struct TmpGuard { double** b; int n; cudaStream_t st; ~TmpGuard() { for (int l = 0; l < n; ++l) if (b[l]) cudaFreeAsync(b[l], st); } } tguard{tb, D.nlev, s};
             c.dense_eval = 0; c.dense_bulk = dense_bulk_default();
-            for (long t0 = 0; t0 < N; t0 += T.N) {
-                const long nc = N - t0 < T.N ? N - t0 : T.N;
+            for (long t0 = 0; t0 < N; t0 += part) {
+                const long nc = N - t0 < part ? N - t0 : part;
                 /* the part's view of the logs and of the temporary store: level 0 is indexed by trajectory, deeper levels through
                  * the slot tables (rows of the whole ensemble) */
-                flint::DenseView lv = a.dv, tv = T.view();
+                flint::DenseView lv = a.dv, tv = a.dv;
                 lv.base[0] += (size_t)t0 * (size_t)D.cap[0] * (size_t)D.rstride;
+                tv.rstride = trs;
+                for (int l = 0; l < D.nlev; ++l) tv.base[l] = tb[l];
                 for (int l = 1; l < D.nlev; ++l) { lv.slot[l] = D.slot[l] + t0; tv.slot[l] = D.slot[l] + t0; }
                 c.N = nc; c.dv = lv; c.dvo = tv; c.dense_count = D.dcount + t0;
                 cudaError_t le = cudaSuccess;
@@ -1292,7 +1309,6 @@ static int interpolate_impl(flint_erk* me, const double* xarr, long G, double* y
                 if (!cuda_ok(flint::launch_interp(b, up, down, sms, s, &nl), "interp launch")) return me->status = FLINT_ERROR;
                 g_launches += nl;
             }
-            if (!cuda_ok(cudaStreamSynchronize(s), "interp execution")) return me->status = FLINT_ERROR;   /* before the temporary store goes */
         } else {
         if (layout == 0) {
             c.dense_eval = 1; c.dvo = c.dv;

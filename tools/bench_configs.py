@@ -65,7 +65,10 @@ if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolat
         return best, ist
 
     for arith in (0, 1):
-        for mode, mname in ((1, "separate"), (0, "fused")):
+        # "logs": Integrate keeps step logs (dense_mode 0); Interpolate goes through a temporary coefficient store in parts of
+        # trajectories (staged, the default) or rebuilds the coefficients in registers and evaluates in the same kernel (fused)
+        for mode, mname in ((1, "separate"), (0, "logs, staged"), (0, "logs, fused")):
+            os.environ["FLINT_B200_DENSE_EVAL"] = "fused" if mname.endswith("fused") else "staged"
             t_int, t_itp, fl_tot, acc_tot, n_ok, n_int_ok = 0.0, [0.0, 0.0], 0.0, 0, 0, 0
             for sh in range(NSH):
                 sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=arith, interp_on=True)
@@ -96,14 +99,15 @@ if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolat
                  frac_fp64_peak=fl_tot / t_int / 1e9 / peak_tf, integrated_fraction=n_int_ok / N)
             for layout in ((0, 1) if mode == 1 else (0,)):
                 rd = gb_r if mode == 1 else gb_log
-                emit(config=4, mode=mname, what="Interpolate onto %d-point grid, layout %d%s" % (G, layout, "" if mode == 1 else " (coefficients rebuilt in registers)"),
+                emit(config=4, mode=mname, what="Interpolate onto %d-point grid, layout %d%s" % (G, layout, "" if mode == 1 else (" (coefficients rebuilt in registers)" if mname.endswith("fused") else " (from step logs, through a temporary coefficient store)")),
                      arith=arith, N=N, shards=NSH, ms=t_itp[layout], yarr_gb=gb_w, read_gb=rd, gbs_written=gb_w / t_itp[layout] * 1e3,
                      gbs_total=(gb_w + rd) / t_itp[layout] * 1e3, frac_hbm_peak_written=gb_w / t_itp[layout] * 1e3 / HBM_GBS,
                      frac_hbm_peak=(gb_w + rd) / t_itp[layout] * 1e3 / HBM_GBS, points_per_s=N * G / t_itp[layout] * 1e3,
                      interpolated_fraction=n_ok / N)
             emit(config=4, mode=mname, what="Integrate + Interpolate [N][G][nI], total", arith=arith, N=N, ms=t_int + t_itp[0],
                  orbits_per_s=N / (t_int + t_itp[0]) * 1e3)
-    if not small:          # the whole of config 4 as one Integrate and one Interpolate call on one GPU (fused path only: it fits)
+    if not small:          # the whole of config 4 as one Integrate and one Interpolate call on one GPU (step logs: they fit)
+        os.environ["FLINT_B200_DENSE_EVAL"] = "staged"
         try:
             N = 1 << 18
             sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=0, interp_on=True)
@@ -113,13 +117,13 @@ if "dense" in which:       # config 4: CR3BP Verner98R, dense output, interpolat
             xarr[-1] = xf
             yarr = torch.empty((N, G, 6), dtype=torch.float64, device="cuda")
             best, ist = timed_interp(erk, xarr, N, 0, yarr)
-            emit(config=4, mode="fused, one call", what="2^18 orbits: one Integrate + one Interpolate call", arith=0, N=N, integrate_ms=ms, interpolate_ms=best,
+            emit(config=4, mode="logs, staged, one call", what="2^18 orbits: one Integrate + one Interpolate call", arith=0, N=N, integrate_ms=ms, interpolate_ms=best,
                  interpolated_fraction=float((ist == 0).float().mean()), yarr_gb=N * G * 48 / 1e9,
                  device_mem_gb=torch.cuda.mem_get_info()[1] / 1e9, orbits_per_s=N / (ms + best) * 1e3)
             del yarr, y0, erk
             gc.collect(); torch.cuda.empty_cache()
         except Exception as e:      # noqa: BLE001
-            emit(config=4, mode="fused, one call", error=str(e)[:300])
+            emit(config=4, mode="logs, staged, one call", error=str(e)[:300])
 
 if "wp" in which:          # config 5: work-precision sweep, spatial CR3BP halo and two-body, all four methods
     N = 1 << (12 if small else 16)
