@@ -251,6 +251,7 @@ static const char* const kErrorStrings[17] = {   /* src/FLINT_base.f90:64-82 */
 extern "C" const char* flint_status_string(int s) { return (s >= 0 && s <= 16) ? kErrorStrings[s] : kErrorStrings[3]; }
 extern "C" const char* flint_last_error(void) { return g_last_error.c_str(); }
 extern "C" long flint_b200_launch_count(void) { return g_launches.load(); }
+extern "C" int flint_b200_bounds_check(void) { return FLINT_BOUNDS_CHECK; }
 extern "C" double flint_b200_last_kernel_ms(void) { return g_last_kernel_ms.load(); }
 extern "C" int flint_b200_device_count(void)
 {

@@ -350,6 +350,7 @@ __device__ __noinline__ void event_rare_path(const SYS& sys, const KArgs& p, EvC
             }
             if (p.ev_rec && c.evcount < p.ev_cap) {                      /* EventData :493 */
                 const long e = c.evcount;
+                FLINT_CHK(e >= 0 && e < p.ev_cap && idx >= 0 && idx < p.N);
                 p.ev_rec[(0 * p.ev_cap + e) * p.N + idx] = EXm[mi][0];
                 for (int i = 0; i < N; ++i) p.ev_rec[((long)(1 + i) * p.ev_cap + e) * p.N + idx] = EYm[i];
                 p.ev_rec[((long)(N + 1) * p.ev_cap + e) * p.N + idx] = (double)(mi + 1);
@@ -550,6 +551,7 @@ template <class SYS> struct Lane {
 template <class SYS>
 __device__ __forceinline__ void state_store(const KArgs& p, long idx, const Lane<SYS>& L, int extra_flags)
 {
+    FLINT_CHK(idx >= 0 && idx < p.scap);
     constexpr int N = SYS::N, M = SYS::M_MAX;
     using D = SD<N, M>;
     const long c = p.scap;
@@ -573,6 +575,7 @@ __device__ __forceinline__ void state_store(const KArgs& p, long idx, const Lane
 template <class SYS>
 __device__ __forceinline__ int state_load(const KArgs& p, long idx, Lane<SYS>& L)
 {
+    FLINT_CHK(idx >= 0 && idx < p.scap);
     constexpr int N = SYS::N, M = SYS::M_MAX;
     using D = SD<N, M>;
     const long c = p.scap;
@@ -807,6 +810,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         sweeps = (n_local + (int)blockDim.x - 1) / (int)blockDim.x;
         for (int j = threadIdx.x; j < n_local; j += blockDim.x) {
             const long i = p.list_in ? (long)p.list_in[lo_item + j] : lo_item + j;
+            FLINT_CHK(lo_item + j < n_items && i < p.N);
             float kf = 2.0f;
             if (i >= 0 && !(p.si[SI::FLAGS * p.scap + i] & kFlagDone)) {
                 const double X0 = p.sd[SD<N, M>::X0 * p.scap + i];
@@ -890,6 +894,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         if ((int)threadIdx.x < s_nsel) {
             jloc = sel[threadIdx.x];
             const long i = p.list_in ? (long)p.list_in[lo_item + jloc] : lo_item + jloc;
+            FLINT_CHK(jloc >= 0 && jloc < n_local && i >= 0 && i < p.N);
             state_load<SYS>(p, i, L);
             idx = i; have = true; powKey = qnan();
         }
@@ -906,6 +911,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
                                                                          the kernel does not depend on how many lanes were launched */
             if (k < n_items) {
                 const long i = p.list_in ? (long)p.list_in[k] : k;
+                FLINT_CHK(i < p.N);
                 if (i >= 0) {
                     const int flags = state_load<SYS>(p, i, L);
                     if (!(flags & kFlagDone)) { idx = i; have = true; powKey = qnan(); }
@@ -942,7 +948,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
         /* ---------------- InterpOn: every level of the dense store full -> suspend; the host adds a level and resumes ---------------- */
         if (have && p.dv.nlev > 0 && L.acc >= p.dense_avail && !(EVMODE == 1 && pending)) {
             state_store<SYS>(p, idx, L, 0);
-            p.ovf_list[atomicAdd(p.n_ovf, 1ULL)] = (int)idx;
+            { const unsigned long long w = atomicAdd(p.n_ovf, 1ULL); FLINT_CHK(w < (unsigned long long)p.N && idx >= 0 && idx < p.N); p.ovf_list[w] = (int)idx; }
             have = false;
             if (GANG) key[jloc] = 2.0f;
         }
@@ -1034,7 +1040,7 @@ erk_step_kernel(const __grid_constant__ KArgs p)
 #pragma unroll
                             for (int i = 0; i < M; ++i) d[(D::EV1 + i) * c] = EV1[i];
                             p.si[SI::DET * c + idx] = (int)det; p.si[SI::SS * c + idx] = (int)ss;
-                            p.list_out[atomicAdd(p.n_out, 1ULL)] = (int)idx;
+                            { const unsigned long long w = atomicAdd(p.n_out, 1ULL); FLINT_CHK(w < (unsigned long long)p.N && idx >= 0 && idx < p.N); p.list_out[w] = (int)idx; }
                             parked = true; have = false;
                             if (GANG) key[jloc] = 2.0f;
                         }
@@ -1094,6 +1100,7 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
     }
     if (j >= n_parked) return;
     const long idx = p.list_in[j];
+    FLINT_CHK(idx >= 0 && idx < p.N);
     SYS sys;
     sys_load(sys, p);
     Lane<SYS> L;

@@ -19,6 +19,7 @@
 #define FLINT_B200_INTERP_EVAL_CUH
 
 #include "arith.cuh"
+#include "kargs.h"
 
 namespace flint {
 
@@ -147,6 +148,7 @@ __device__ __forceinline__ void eval_point_range(const double* __restrict__ sB, 
         { const long gq = g + n + lane; xn = gq < gend ? xarr[gq] : 0.0; }
         if (lane < n) {
             const int ii = i + (gl >= mid ? 1 : 0);
+            FLINT_CHK(ii >= 0 && ii < ns && gl >= 0 && gl < G);
             const double X0 = sX[ii], X1 = sX[ii + 1];
             const double* __restrict__ B = sB + (long)ii * rsp;
             const double h = X1 - X0;

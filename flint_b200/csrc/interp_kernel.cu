@@ -573,6 +573,9 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                     base += __shfl_sync(0xffffffffu, inc, 31);
                 }
                 if (lane == 0 && ns == kItemsSteps) row[kItemsSteps] = make_int2(g[NB], base);
+                FLINT_CHK(ns >= 1 && ns <= kItemsSteps && t >= 0 && t < a.N && s0 >= 0 && s0 + ns <= acc && base >= 0);
+#pragma unroll
+                for (int u = 0; u <= NB; ++u) FLINT_CHK(g[u] >= 0 && g[u] <= a.G);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready + s);                 /* release: the consumers acquire with their wait */
                 ++k_done;
@@ -667,6 +670,8 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
             if (!valid) { ga = ge; len = 0; }
             const int wbase = __shfl_sync(0xffffffffu, ga, 0);
             const int wend = __shfl_sync(0xffffffffu, ga + len, 31);   /* items are consecutive in point order; invalid lanes sit at the end */
+            FLINT_CHK(t >= 0 && t < a.N && i >= 0 && i < ns && len >= 0 && ga >= wbase && ga + len <= wend && wend <= a.G &&
+                      wend - wbase <= 32 * P && e0.y <= kk && kk < row[i + 1].y + (valid ? 0 : 1));
             double xs[P];
 #pragma unroll
             for (int j = 0; j < P; ++j) xs[j] = j < len ? xg[ga + j] : 0.0;

@@ -41,6 +41,19 @@
 
 #define FLINT_DENSE_LEVELS 6          /* capacity levels of the dense-output store (each 4x the one before) */
 
+/* FLINT_BOUNDS_CHECK=1 (python -m flint_b200.build --tag _chk -D FLINT_BOUNDS_CHECK=1): every index into the work lists, the
+ * state block, the event records, the dense store and the interpolation kernels' shared-memory buffers is tested on the device
+ * and the kernel traps on the first one out of range -- the stand-in for compute-sanitizer's memcheck, which is closed on the
+ * GPU pool this was developed on.  The GPU test-suite runs clean under that build (profiles/r02_bounds_check.log). */
+#ifndef FLINT_BOUNDS_CHECK
+#define FLINT_BOUNDS_CHECK 0
+#endif
+#if FLINT_BOUNDS_CHECK && defined(__CUDA_ARCH__)
+#define FLINT_CHK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define FLINT_CHK(cond) ((void)0)
+#endif
+
 namespace flint {
 
 /* ---- dense-output storage (InterpOn; src/ERKIntegrate.f90:555-566,660-676; src/ERKInit.f90:321-332).
@@ -64,8 +77,10 @@ struct DenseView {
     __host__ __device__ __forceinline__ double* rec(long t, long a) const
     {
         int l = 0;
+        FLINT_CHK(t >= 0 && a >= 0 && nlev > 0 && a < cum[nlev]);
         while (l + 1 < nlev && a >= cum[l + 1]) ++l;
         const long row = l == 0 ? t : (long)slot[l][t];
+        FLINT_CHK(row >= 0);
         return base[l] + (row * (cum[l + 1] - cum[l]) + (a - cum[l])) * (long)rstride;
     }
     __host__ __device__ __forceinline__ long capacity() const { return nlev > 0 ? cum[nlev] : 0; }

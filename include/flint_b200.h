@@ -256,6 +256,8 @@ int flint_b200_device_count(void);
 double flint_b200_measure_fp64_peak(int device, double* sm_clock_mhz_out);
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 long flint_b200_launch_count(void);
+/* 1 when the library was built with -D FLINT_BOUNDS_CHECK=1 (every device-side index tested, trap on the first one out of range) */
+int flint_b200_bounds_check(void);
 /* Last integrate kernel's duration in ms measured with CUDA events on the launch stream (batch calls). */
 double flint_b200_last_kernel_ms(void);
 /* Device self-test of the branch-free division / square-root helpers the right-hand sides use
