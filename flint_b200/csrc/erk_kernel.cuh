@@ -1157,11 +1157,12 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     const long t = blockIdx.x;
     const long ntot = p.dense_count[t];
     const long nacc = ntot < p.dv.capacity() ? ntot : p.dv.capacity();
-    const long s0 = (long)blockIdx.y * kDenseBlock;
-    if (s0 >= nacc) return;
     if (p.dense_eval && p.istatus[t] != FLINT_SUCCESS) return;       /* this trajectory's grid failed the validation (:60-76) */
-    const int ns = (int)(nacc - s0 < kDenseBlock ? nacc - s0 : kDenseBlock);
     const int tid = threadIdx.x;
+    /* gridDim.y covers level 0 of the store (launch_dense); the few trajectories that grew deeper levels have their further blocks
+     * dealt round-robin over the same CTAs, instead of every trajectory paying empty CTAs for the deepest level anyone reached */
+    for (long s0 = (long)blockIdx.y * kDenseBlock; s0 < nacc; s0 += (long)gridDim.y * kDenseBlock) {
+    const int ns = (int)(nacc - s0 < kDenseBlock ? nacc - s0 : kDenseBlock);
     extern __shared__ __align__(16) double dsm[];
     const int rs = (PS + 1) * p.nI, rsp = rs + (rs & 1);
     double* sB = dsm;                                       /* [128][rsp] */
@@ -1237,8 +1238,9 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      /* shared memory may go once it has been read */
         }
+        __syncthreads();                                    /* ... and be written again by the next block of this CTA */
         }
-        return;
+        continue;
     }
     __syncthreads();
     const double hs = sign1(sX[1] - sX[0]);                 /* every step points in the direction of integration */
@@ -1253,6 +1255,8 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     case 5: eval_block_steps<FMA, PS, 5, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
     case 6: if constexpr (N >= 6) eval_block_steps<FMA, PS, 6, false>(sB, rsp, sX, sG, ns, xg, p.iG, yo, 0); break;
     default: break;
+    }
+    __syncthreads();                                        /* the next block of this CTA overwrites what was just read */
     }
 }
 

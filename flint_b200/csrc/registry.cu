@@ -126,6 +126,10 @@ cudaError_t launch_dense(const KernelEntry& e, bool plane, const KArgs& a, cudaS
     const long cap = a.dv.capacity();
     long gy = (cap + kDenseBlock - 1) / kDenseBlock;
     if (gy < 1) gy = 1;
+    {   /* blocks of level 0 only: deeper levels hold a few trajectories, whose CTAs walk their further blocks (erk_dense_kernel) */
+        const long gy0 = (a.dv.nlev > 0 ? a.dv.cum[1] : cap) / kDenseBlock;
+        if (gy0 >= 1 && gy > gy0) gy = gy0;
+    }
     if (gy > 65535) return cudaErrorInvalidConfiguration;
     /* fused evaluation: coefficients + ranges; otherwise the block's records, staged for one bulk store (erk_dense_kernel) */
     const int smem = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : (a.dense_bulk ? kDenseBlock * a.dvo.rstride * 8 : 0);
