@@ -1154,16 +1154,49 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
      * plane variant skips the stage sums of the identically +0 components and forms their coefficients from +0 stage
      * values with the general expressions, so the zeros carry the same signs */
     if (p.zflag && ((*p.zflag != 0) != is_plane_variant<SYS>())) return;
-    const long t = blockIdx.x;
-    const long ntot = p.dense_count[t];
-    const long nacc = ntot < p.dv.capacity() ? ntot : p.dv.capacity();
-    if (p.dense_eval && p.istatus[t] != FLINT_SUCCESS) return;       /* this trajectory's grid failed the validation (:60-76) */
     const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double dsm[];
+    /* A CTA serves the trajectories blockIdx.x, blockIdx.x + gridDim.x, ...: a thread lives for one step (~10 us of arithmetic)
+     * and used to spend a fifth of that waiting for its log (step count -> record, two DRAM round trips; ncu: 22 % of the stall
+     * samples).  Now the NEXT trajectory's step count and this thread's log record of it travel (cp.async, into a slot of shared
+     * memory behind the kernel's other buffers) while the current step is computed. */
+    double* pf = dsm + ((p.dense_eval ? dense_smem_doubles_ps(PS, p.nI) : (p.dense_bulk ? kDenseBlock * p.dvo.rstride : 0)) + 1) / 2 * 2;
+    double* myslot = pf + tid * kDensePfSlot;
+    int* pfcount = reinterpret_cast<int*>(pf + kDenseBlock * kDensePfSlot);       /* [2]: step counts, alternating */
+    const long cap0 = p.dv.cum[1];
+    constexpr int nlog = 2 * N + 2;                                   /* X, h, Y, F0 (an event log's further fields: from the store, rare) */
+    static_assert(nlog % 2 == 0 && nlog <= kDensePfSlot - 2, "a log fits its prefetch slot in 16-byte units");
+    auto prefetch = [&](long tn, int par) {
+        if (tn < p.N) {
+            const double* src = p.dv.base[0] + (tn * cap0 + (long)blockIdx.y * kDenseBlock + tid) * (long)p.dv.rstride;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(myslot);
+#pragma unroll
+            for (int q = 0; q < nlog; q += 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + q * 8), "l"(src + q));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (kDensePfSlot - 2) * 8), "l"(src + p.dv.rstride - 1));
+            if (tid == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(pfcount + par)), "l"(p.dense_count + tn));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int par = 0;
+    prefetch((long)blockIdx.x, par);
+    for (long t = blockIdx.x; t < p.N; t += gridDim.x, par ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                                  /* the step count thread 0 fetched; everybody is done with the previous trajectory */
+    const long ntot = pfcount[par];
+    const long nacc = ntot < p.dv.capacity() ? ntot : p.dv.capacity();
+    /* this thread's log of the first block, out of its slot, before the next prefetch overwrites it */
+    double lg[nlog], lkind;
+#pragma unroll
+    for (int q = 0; q < nlog; ++q) lg[q] = myslot[q];
+    lkind = myslot[kDensePfSlot - 2];
+    __syncwarp();
+    prefetch(t + gridDim.x, par ^ 1);
+    if (p.dense_eval && p.istatus[t] != FLINT_SUCCESS) continue;      /* this trajectory's grid failed the validation (:60-76) */
     /* gridDim.y covers level 0 of the store (launch_dense); the few trajectories that grew deeper levels have their further blocks
      * dealt round-robin over the same CTAs, instead of every trajectory paying empty CTAs for the deepest level anyone reached */
     for (long s0 = (long)blockIdx.y * kDenseBlock; s0 < nacc; s0 += (long)gridDim.y * kDenseBlock) {
+    const bool first_blk = s0 == (long)blockIdx.y * kDenseBlock;     /* its logs are in lg[]; deeper blocks read the store */
     const int ns = (int)(nacc - s0 < kDenseBlock ? nacc - s0 : kDenseBlock);
-    extern __shared__ __align__(16) double dsm[];
     const int rs = (PS + 1) * p.nI, rsp = rs + (rs & 1);
     double* sB = dsm;                                       /* [128][rsp] */
     double* sX = dsm + kDenseBlock * rsp;                   /* [129] (+1 pad) */
@@ -1173,8 +1206,8 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     sys_load(sys, p);
     if (tid < ns) {
         const double* __restrict__ rec = p.dv.rec(t, s0 + tid);
-        const double kind = rec[p.dv.rstride - 1];
-        const double X = rec[0], h = rec[1];                /* a coefficient record: X0, X1 */
+        const double kind = first_blk ? lkind : rec[p.dv.rstride - 1];
+        const double X = first_blk ? lg[0] : rec[0], h = first_blk ? lg[1] : rec[1];                /* a coefficient record: X0, X1 */
         if (kind == kDenseCoef) {                           /* built by an earlier pass */
             if (p.dense_eval) {
                 sX[tid] = X; if (tid == ns - 1) sX[ns] = h;
@@ -1188,10 +1221,10 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
         } else {
             double Y[N], F0[N], Y1[N], Yn[N], Yp[N], e, B[PS + 1][N];
 #pragma unroll
-            for (int c = 0; c < N; ++c) { Y[c] = rec[2 + c]; F0[c] = rec[2 + N + c]; }
+            for (int c = 0; c < N; ++c) { Y[c] = first_blk ? lg[2 + c] : rec[2 + c]; F0[c] = first_blk ? lg[2 + N + c] : rec[2 + N + c]; }
             double h_stage = h;
             const bool ev = kind == kDenseEvLog;
-            if (ev) {
+            if (ev) {                                       /* rare: straight from the store */
                 h_stage = rec[2 + 2 * N];
 #pragma unroll
                 for (int c = 0; c < N; ++c) Y1[c] = rec[3 + 2 * N + c];
@@ -1258,6 +1291,8 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
     }
     __syncthreads();                                        /* the next block of this CTA overwrites what was just read */
     }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 #ifndef __CUDACC_RTC__

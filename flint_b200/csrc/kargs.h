@@ -159,6 +159,11 @@ __host__ __device__ constexpr int dense_smem_doubles_ps(int pstar, int nI)
     return kDenseBlock * (rs + (rs & 1)) + 2 * (kDenseBlock + 2);
 }
 
+/* erk_dense_kernel: a CTA walks trajectories blockIdx.x, blockIdx.x + gridDim.x, ... and prefetches the next one's step logs
+ * (cp.async) into a per-thread slot of kDensePfSlot doubles at the end of its dynamic shared memory, + two step counts */
+constexpr int kDensePfSlot = 26;                       /* 22 doubles of log (3n+3 <= 21 for n <= 6), the kind, padding: 13 x 16 bytes */
+__host__ __device__ constexpr int dense_prefetch_doubles() { return kDenseBlock * kDensePfSlot + 2; }
+
 struct InterpArgs {
     long N, G;
     int nI, pstar;

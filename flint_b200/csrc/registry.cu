@@ -136,12 +136,21 @@ cudaError_t launch_dense(const KernelEntry& e, bool plane, const KArgs& a, cudaS
     }
     if (gy > 65535) return cudaErrorInvalidConfiguration;
     /* fused evaluation: coefficients + ranges; otherwise the block's records, staged for one bulk store (erk_dense_kernel) */
-    const int smem = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : (a.dense_bulk ? kDenseBlock * a.dvo.rstride * 8 : 0);
+    const int smem_main = a.dense_eval ? dense_smem_doubles_ps(e.pstar, a.nI) * 8 : (a.dense_bulk ? kDenseBlock * a.dvo.rstride * 8 : 0);
+    const int smem = (smem_main + 15) / 16 * 16 + dense_prefetch_doubles() * 8;       /* + the prefetch slots (erk_dense_kernel) */
     if (smem > 48 * 1024) {
         const cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (er != cudaSuccess) return er;
     }
-    return launch_kernel(k, a, dim3((unsigned)a.N, (unsigned)gy), kDenseBlock, (size_t)smem, s);
+    /* a CTA serves several trajectories in turn (the next one's logs travel while it computes): ~8 per CTA, at least one
+     * resident wave */
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long gx = (a.N + 7) / 8;
+    const long wave = ((long)sms * 3 + gy - 1) / gy;
+    if (gx < wave) gx = wave;
+    if (gx > a.N) gx = a.N;
+    return launch_kernel(k, a, dim3((unsigned)gx, (unsigned)gy), kDenseBlock, (size_t)smem, s);
 }
 
 /* work counters of one Integrate chunk, written in stream order (a pageable host-to-device copy would make the host wait
