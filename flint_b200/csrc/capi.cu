@@ -672,7 +672,6 @@ static int integrate_impl(flint_erk* me, long N, double x0_scalar, const double*
                 return me->status = FLINT_ERROR;
         me->pipe_device = ex.device;
     }
-    const size_t szT = (size_t)sh.Ntot;                            /* row pitch (elements) of the caller's SoA arrays */
     if (!me->pinned && !cuda_ok(cudaHostAlloc((void**)&me->pinned, 64, cudaHostAllocDefault), "cudaHostAlloc")) return me->status = FLINT_ERROR;
 
     /* one chunk [off, off + cnt) of the ensemble on stream s with the buffers of pipeline slot `slot` */
