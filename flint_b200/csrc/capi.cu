@@ -523,8 +523,8 @@ static bool shard_copy(const Shard& sh, long N, long off, long cnt, void* dst, c
  * (FLINT_B200_DENSE_BULK=0; kept for comparison, profiles/r02_notes.md) */
 static int dense_bulk_default()
 {
-    static const int v = [] { const char* e = getenv("FLINT_B200_DENSE_BULK"); return e ? atoi(e) : 0; }();
-    return v;
+    const char* e = getenv("FLINT_B200_DENSE_BULK");
+    return e ? atoi(e) : 1;
 }
 
 /* what Init parsed, as the kernels' parameter block (everything that does not depend on one Integrate call) */

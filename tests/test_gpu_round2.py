@@ -348,6 +348,26 @@ def test_staged_and_fused_evaluation_from_step_logs(method, cap, monkeypatch):
         K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr from step logs, per-trajectory grids, %s, method %d" % (how, method))
 
 
+@pytest.mark.parametrize("bulk", ["0", "1"])
+def test_coefficient_records_thread_by_thread_and_as_bulk_stores(bulk, monkeypatch):
+    """erk_dense_kernel writes a block's coefficient records with one bulk store from shared memory (default) or thread by thread
+    (FLINT_B200_DENSE_BULK=0): same records, same Yarr, with the in-place pass of Integrate (dense_mode 1) and with the temporary
+    store of the staged Interpolate (dense_mode 0); DOP54's store grows two levels from 128 steps."""
+    monkeypatch.setenv("FLINT_B200_DENSE_BULK", bulk)
+    for method, cap in ((F.ERK_VERNER65E, 256), (F.ERK_DOP54, 128)):
+        case = K.cr3bp_case(method, 1e-9, 1, interp_on=True, eventset=F.FLINT_EVSET_NONE)
+        N, G = 300, 777
+        y0 = P.cr3bp_ensemble(N, start=4096)
+        xarr = np.linspace(0.0, case.xf, G); xarr[-1] = case.xf
+        o = case.run_oracle(y0, xarr=xarr)
+        for dense_mode in (1, 0):
+            g = case.run_gpu(y0, dense_mode=dense_mode, dense_cap=cap)
+            ok = g["status"] == 0
+            st, yarr, ist = g["erk"].InterpolateBatch(xarr, N)
+            assert st == 0 and ok.sum() > N // 2 and (ist[ok] == 0).all()
+            K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr, bulk %s, dense_mode %d, method %d" % (bulk, dense_mode, method))
+
+
 def test_per_trajectory_grids():
     """flint_erk_interpolate_batch_grids: one grid per trajectory (ragged spans: every trajectory has its own Xf), a backward
     ensemble, and a row that leaves its trajectory's span (FLINT_ERROR_INTP_ARRAY for that trajectory only)."""
