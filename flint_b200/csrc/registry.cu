@@ -93,11 +93,10 @@ cudaError_t launch_step(const StepKernel& k, const KArgs& a, int sm_count, long 
     { const cudaError_t e = resident_ctas(k.classic, block, smem, &bps); if (e != cudaSuccess) return e; }
     if (bps_req > 0 && bps_req < bps) bps = bps_req;
     long grid = (long)sm_count * bps;                       /* persistent lanes: one resident wave */
-    /* a pass much smaller than the device (resumed stragglers, the trajectories a new level of the dense store was added for):
-     * four items per CTA instead of a full CTA's worth, so that it spreads over the SMs -- a warp that has a scheduler to itself
-     * runs a step attempt five times faster than one of sixteen on a full SM (profiles/r02_notes.md) */
-    const long per_cta = n_items * 8 < grid * block ? 4 : block;
-    const long need = (n_items + per_cta - 1) / per_cta;
+    /* a pass smaller than the device keeps its lanes PACKED (full warps on few SMs): a warp costs the same issue slots whatever
+     * the number of its active lanes, and one warp per scheduler is as fast as a warp gets -- spreading 4096 trajectories as four
+     * per CTA was measured 1.7x slower (profiles/r02_notes.md) */
+    const long need = (n_items + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (k.gang) {
