@@ -219,20 +219,25 @@ __global__ void __launch_bounds__(kStepsThreads, kStepsResident) interp_steps_ke
     const long t = blockIdx.x;
     if (a.status[t] != FLINT_SUCCESS) return;                          /* validated before (launch_interp) */
     const long acc = a.dcount[t];
-    const long s0 = (long)blockIdx.y * kStepsBlock;
-    if (s0 >= acc) return;
-    const int ns = (int)(acc - s0 < kStepsBlock ? acc - s0 : kStepsBlock);
     const int rstride = a.dv.rstride;
     extern __shared__ __align__(128) double ssm[];
     double* sR = ssm;                                                  /* [128][rstride]: the records as they lie in HBM */
     double* sX = ssm + kStepsBlock * rstride;                          /* [129] (+1 pad) */
     long* sG = reinterpret_cast<long*>(sX + kStepsBlock + 2);          /* [129] */
     uint64_t* bar = reinterpret_cast<uint64_t*>(sG + kStepsBlock + 2);
-    const double* __restrict__ src = a.dv.rec(t, s0);
-    const unsigned bytes = (unsigned)ns * (unsigned)rstride * 8u;      /* a multiple of 16: rstride is even */
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    /* gridDim.y covers level 0 of the store (launch_steps_one); a trajectory that grew deeper levels has its further blocks dealt
+     * round-robin over its CTAs */
+    unsigned phase = 0;
+    for (long s0 = (long)blockIdx.y * kStepsBlock; s0 < acc; s0 += (long)gridDim.y * kStepsBlock, phase ^= 1u) {
+    const int ns = (int)(acc - s0 < kStepsBlock ? acc - s0 : kStepsBlock);
+    const double* __restrict__ src = a.dv.rec(t, s0);
+    const unsigned bytes = (unsigned)ns * (unsigned)rstride * 8u;      /* a multiple of 16: rstride is even */
+    __syncthreads();                                                   /* the barrier is initialised; the previous block's buffers are free */
+    if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sR)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -247,12 +252,13 @@ __global__ void __launch_bounds__(kStepsThreads, kStepsResident) interp_steps_ke
     {
         unsigned ok = 0;
         do {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(smem_u32(bar)) : "memory");
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
         } while (!ok);
     }
     double* yo = SOA ? a.yarr + t : a.yarr + t * a.G * NI;            /* [nI][G][N]: this trajectory's column */
     eval_block_steps<FMA, PS, NI, SOA>(sR + 2, rstride, sX, sG, ns, xg, a.G, yo, a.N);
+    }
 }
 
 /* ======================================================================================================
@@ -820,8 +826,10 @@ template <bool FMA, int PS, int NI>
 static cudaError_t launch_steps_one(const InterpArgs& a, cudaStream_t s)
 {
     const long cap = a.dv.capacity();
-    const long gy = (cap + kStepsBlock - 1) / kStepsBlock;
-    if (gy < 1 || gy > 65535) return cudaErrorInvalidConfiguration;
+    long gy = (cap + kStepsBlock - 1) / kStepsBlock;
+    if (gy < 1) return cudaErrorInvalidConfiguration;
+    { const long gy0 = a.dv.cum[1] / kStepsBlock; if (gy0 >= 1 && gy > gy0) gy = gy0; }   /* level 0; deeper blocks: the kernel's loop */
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
     const int smem = (kStepsBlock * a.dv.rstride + 2 * (kStepsBlock + 2) + 2) * 8;
     const dim3 grid((unsigned)a.N, (unsigned)gy);
     if (a.layout == 0) {
