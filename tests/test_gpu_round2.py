@@ -368,6 +368,34 @@ def test_coefficient_records_thread_by_thread_and_as_bulk_stores(bulk, monkeypat
             K.assert_bit_equal(yarr[ok], o["yarr"][ok], "Yarr, bulk %s, dense_mode %d, method %d" % (bulk, dense_mode, method))
 
 
+def test_interpolation_edge_grids(monkeypatch):
+    """Grids the thread-per-item kernel's planning has to get right: one, two and three points; every point inside the first step;
+    every point inside the last step; the exact ends of the span; forward and backward integration."""
+    for sign in (1.0, -1.0):
+        case = K.twobody_case(F.ERK_DOP853, 1e-10, 0, nper=1, interp_on=True)
+        N = 40
+        y0 = P.perturbed_ensemble(P.TBP_Y0, N)
+        xf = sign * 0.9 * P.tbp_period()
+        case.xf = xf
+        g = case.run_gpu(y0, dense_mode=1)
+        sc = case.oracle_scalar()
+        grids = [np.array([0.37 * xf]), np.array([0.0, xf]), np.array([0.0, 0.5 * xf, xf]),
+                 np.linspace(0.0, 1e-7 * xf, 9), np.linspace((1.0 - 1e-7) * xf, xf, 9), np.array([xf]), np.array([0.0])]
+        for kern in ("items", "steps"):
+            monkeypatch.setenv("FLINT_B200_INTERP_KERNEL", kern)
+            for xarr in grids:
+                xarr = xarr.copy()
+                if len(xarr) > 1: xarr[-1] = xarr[-1] if abs(xarr[-1]) < abs(xf) else xf
+                st, yarr, ist = g["erk"].InterpolateBatch(xarr, N, SaveInterpCoeffs=True)
+                assert st == 0 and (ist == 0).all(), (kern, xarr, ist)
+                for t in (0, 13, N - 1):
+                    sc.integrate(0.0, y0[:, t], float(xf), io=case.oracle_int())
+                    so, yo = sc.interpolate(xarr, save=True)
+                    assert so == 0
+                    K.assert_bit_equal(yarr[t], yo, "edge grid %s, kernel %s, trajectory %d" % (xarr[:3], kern, t))
+        monkeypatch.delenv("FLINT_B200_INTERP_KERNEL")
+
+
 def test_per_trajectory_grids():
     """flint_erk_interpolate_batch_grids: one grid per trajectory (ragged spans: every trajectory has its own Xf), a backward
     ensemble, and a row that leaves its trajectory's span (FLINT_ERROR_INTP_ARRAY for that trajectory only)."""
