@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
 
     if (warp == 0) {
         /* ------------------------------ helper: bulk copies ahead, ranges and items of what has landed ------------------------------ */
-        constexpr int NB = kItemsSteps / 32;                            /* boundaries per lane (+ the last one, on every lane) */
+        constexpr int NB = kItemsSteps / 32;                            /* boundaries per lane: lane + 1 + 32 u, u < NB (1 .. kItemsSteps) */
         long k_issue = 0, k_probe = 0, k_done = 0;                      /* tiles whose copy was issued / whose searches are in flight / published */
         /* the trajectories of this CTA, 32 at a time: step counts (0: none / failed grid) one batch ahead of their use */
         long tb = blockIdx.x;                                           /* first trajectory of the current batch */
@@ -512,9 +512,12 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
         long cur_t = -1, cur_acc = 0, cur_s0 = 0;                       /* trajectory being dealt, next step to issue */
         bool more = true;
         double xa = 0.0, xb = 0.0, inv_span = 0.0; long x_t = -2;       /* grid ends of the trajectory whose grid is loaded */
-        /* the searches of up to TWO tiles are in flight (prA: the older), so a tile's loads have a whole turn of the loop to arrive */
-        GridProbe prA[NB + 1], prB[NB + 1];
+        /* the searches of up to TWO tiles are in flight (prA: the older), so a tile's loads have a whole turn of the loop to arrive.
+         * A tile's first boundary is the last one of the tile before it (same trajectory, published just before) or the start of
+         * the trajectory: it is carried, not searched -- kItemsSteps searches per tile on 32 lanes, NB rounds */
+        GridProbe prA[NB], prB[NB];
         int n_fly = 0;
+        int g_carry = 0;                                                /* first grid point of the next tile's first step */
         /* The helper never blocks on a barrier: a tile that has not landed, or a buffer that is not free yet, is looked at again in
          * the next turn of the loop, so that publishing what is ready never waits for either */
         while (more || k_done < k_issue) {
@@ -531,8 +534,8 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                 const long xt = a.per_traj ? t : -1;
                 if (xt != x_t) { xa = xg[0]; xb = xg[a.G - 1]; inv_span = 1.0 / (xb - xa); x_t = xt; }
 #pragma unroll
-                for (int u = 0; u <= NB; ++u) {
-                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
+                for (int u = 0; u < NB; ++u) {
+                    const int i = lane + 1 + 32 * u;                       /* boundary i = end of step i - 1 */
                     const double X = i < ns ? sR[(long)i * rsp] : (i == ns ? sR[(long)(ns - 1) * rsp + 1] : xa);
                     if (n_fly == 0) grid_probe_issue(prA[u], xg, a.G, X, xa, inv_span);
                     else grid_probe_issue(prB[u], xg, a.G, X, xa, inv_span);
@@ -553,41 +556,43 @@ __global__ void __launch_bounds__(kItemsThreads, 1) interp_items_kernel(InterpAr
                 const double hs = sign1(sR[1] - sR[0]);                  /* records are (X0, X1, ...): every step points in the direction of integration */
                 double ta = xa, tb2 = xb;                                 /* a per-trajectory grid: the ends of THIS tile's grid (the newer tile may have another) */
                 if (a.per_traj && x_t != t) { ta = xg[0]; tb2 = xg[a.G - 1]; }
-                int g[NB + 1];
-#pragma unroll
-                for (int u = 0; u <= NB; ++u) {
-                    const int i = u < NB ? lane + 32 * u : kItemsSteps;
-                    bool ok;
-                    const long r = grid_probe_result(prA[u], a.G, hs, ta, tb2, ok);
-                    if (i > ns) g[u] = 0;
-                    else if (i == 0 && s0 == 0) g[u] = 0;
-                    else if (i == ns && s0 + ns == acc) g[u] = (int)a.G;
-                    else g[u] = (int)(ok ? r : grid_count_upto(xg, a.G, hs, prA[u].X));
-                }
-                int base = 0;                                             /* items of the steps before this group of 32 */
+                int ge[NB];                                               /* first grid point beyond step lane + 32 u (= boundary lane + 1 + 32 u) */
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
-                    int nxt = __shfl_down_sync(0xffffffffu, g[u], 1);
-                    const int g_up = __shfl_sync(0xffffffffu, g[u + 1 < NB ? u + 1 : u], 0);
-                    if (lane == 31) nxt = u + 1 < NB ? g_up : g[NB];
-                    const int i = lane + 32 * u;
-                    const int c = i < ns ? (nxt - g[u] + P - 1) / P : 0;   /* items of step i */
+                    const int i = lane + 1 + 32 * u;
+                    bool ok;
+                    const long r = grid_probe_result(prA[u], a.G, hs, ta, tb2, ok);
+                    if (i > ns) ge[u] = 0;
+                    else if (i == ns && s0 + ns == acc) ge[u] = (int)a.G;
+                    else ge[u] = (int)(ok ? r : grid_count_upto(xg, a.G, hs, prA[u].X));
+                }
+                const int g0 = s0 == 0 ? 0 : g_carry;                     /* boundary 0 */
+                int base = 0;                                             /* items of the steps before this group of 32 */
+                int prev_last = g0;                                       /* boundary 32 u: the end of the group before */
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    int gs = __shfl_up_sync(0xffffffffu, ge[u], 1);       /* start of step lane + 32 u */
+                    if (lane == 0) gs = prev_last;
+                    const int i = lane + 32 * u;                          /* this lane's step */
+                    const int c = i < ns ? (ge[u] - gs + P - 1) / P : 0;  /* its items */
                     int inc = c;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-                    if (i <= ns) row[i] = make_int2(g[u], base + inc - c);
+                    if (i < ns) row[i] = make_int2(gs, base + inc - c);
+                    if (i == ns - 1) row[ns] = make_int2(ge[u], base + inc);      /* the end of the tile: last boundary, number of items */
                     base += __shfl_sync(0xffffffffu, inc, 31);
+                    prev_last = __shfl_sync(0xffffffffu, ge[u], 31);
                 }
-                if (lane == 0 && ns == kItemsSteps) row[kItemsSteps] = make_int2(g[NB], base);
-                FLINT_CHK(ns >= 1 && ns <= kItemsSteps && t >= 0 && t < a.N && s0 >= 0 && s0 + ns <= acc && base >= 0);
+                g_carry = prev_last;                                      /* boundary kItemsSteps (used only when the trajectory goes on: ns == kItemsSteps) */
+                FLINT_CHK(ns >= 1 && ns <= kItemsSteps && t >= 0 && t < a.N && s0 >= 0 && s0 + ns <= acc && base >= 0 && g0 >= 0 && g0 <= a.G);
 #pragma unroll
-                for (int u = 0; u <= NB; ++u) FLINT_CHK(g[u] >= 0 && g[u] <= a.G);
+                for (int u = 0; u < NB; ++u) FLINT_CHK(ge[u] >= 0 && ge[u] <= a.G);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready + s);                 /* release: the consumers acquire with their wait */
                 ++k_done;
                 --n_fly;
 #pragma unroll
-                for (int u = 0; u <= NB; ++u) prA[u] = prB[u];
+                for (int u = 0; u < NB; ++u) prA[u] = prB[u];
             }
             /* (3) the next tile's copy, as soon as its buffer is free (the tile kItemsStages before it consumed) */
             if (more && k_issue - k_done < S && (k_issue < S || mbar_test(bar_empty + (int)(k_issue % S), (unsigned)((k_issue / S - 1) & 1)))) {
