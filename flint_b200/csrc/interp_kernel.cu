@@ -438,13 +438,13 @@ __global__ void __launch_bounds__(kTileThreads, FLINT_TILE_CTAS) interp_tiles_ke
  * The kernel is persistent (one CTA per SM, trajectories dealt round-robin, a trajectory's tiles of 64 consecutive steps in
  * sequence) and warp-specialised.  Warp 0 is the HELPER: up to kItemsStages tiles ahead it issues the bulk copy of a tile's
  * records (completion on an mbarrier); for a tile that has landed it reads the step boundaries from shared memory and starts
- * the search for the first grid point of every step -- 65 boundaries on 32 lanes, three searches side by side, one round of
- * loads each for a near-uniform grid (grid_probe_issue); the searches of two tiles are in flight, and the older one is finished
+ * the search for the first grid point of every step -- 64 boundaries on 32 lanes (the tile's first one is carried from the tile
+ * before it), one round of loads each for a near-uniform grid (grid_probe_issue); the searches of two tiles are in flight, and the older one is finished
  * (grid_probe_result, warp scan for the first item of every step) and published on a second mbarrier.  The helper never blocks
  * on a barrier.  The eleven CONSUMER warps deal the 32-item rounds of the tile stream among themselves round-robin and wait
  * for nothing but the "tile planned" barrier.
  *
- * Measured (2^15 orbits x 10^4 points x 6 states, Verner98R, profiles/r02_notes.md): 5.78 -> 4.68 ms strict, 5.68 -> 4.40 ms
+ * Measured (2^15 orbits x 10^4 points x 6 states, Verner98R, profiles/r02_notes.md): 5.78 -> 4.64 ms strict, 5.68 -> 4.15 ms
  * FMA against interp_steps_kernel.  Measured and dropped: a separate planning kernel (0.73 ms: 8 useful bytes per 64 fetched),
  * one bulk copy per record into padded slots (TMA issue-bound), the next round's search and x loads one round ahead (spills,
  * 6.3 ms), theta from a reciprocal of h kept per item (5.2 ms: the range check and fall-back per point cost more than the five
