@@ -402,14 +402,17 @@ __device__ __forceinline__ void store_coef_record(double* __restrict__ rec, int 
 #pragma unroll
                 for (int cc = 0; cc < N; ++cc) c[j * N + cc] = B[j][cc];
         }
-    } else {
-        for (int j = 0; j <= PS; ++j)
-            for (int ii = 0; ii < nI; ++ii) {
+    } else {                           /* a subset (InterpStates): B is only ever indexed with constants, so it stays in registers */
+        for (int ii = 0; ii < nI; ++ii) {
+            const int want = istates[ii] - 1;
+#pragma unroll
+            for (int j = 0; j <= PS; ++j) {
                 double v = 0.0;
 #pragma unroll
-                for (int cc = 0; cc < N; ++cc) if (istates[ii] - 1 == cc) v = B[j][cc];
+                for (int cc = 0; cc < N; ++cc) if (want == cc) v = B[j][cc];
                 c[j * nI + ii] = v;
             }
+        }
     }
     rec[rstride - 1] = kDenseCoef;
 }
@@ -1245,13 +1248,16 @@ __global__ void __launch_bounds__(kDenseBlock, FLINT_DENSE_MIN_BLOCKS(METHOD)) e
 #pragma unroll
                         for (int c = 0; c < N; ++c) sB[tid * rsp + j * N + c] = B[j][c];
                 } else {
-                    for (int j = 0; j <= PS; ++j)
-                        for (int ii = 0; ii < p.nI; ++ii) {
+                    for (int ii = 0; ii < p.nI; ++ii) {
+                        const int want = p.istates[ii] - 1;
+#pragma unroll
+                        for (int j = 0; j <= PS; ++j) {
                             double v = 0.0;
 #pragma unroll
-                            for (int c = 0; c < N; ++c) if (p.istates[ii] - 1 == c) v = B[j][c];
+                            for (int c = 0; c < N; ++c) if (want == c) v = B[j][c];
                             sB[tid * rsp + j * p.nI + ii] = v;
                         }
+                    }
                 }
             } else store_coef_record<METHOD, SYS>(p.dense_bulk ? dsm + (long)tid * p.dvo.rstride : p.dvo.rec(t, s0 + tid), p.dvo.rstride,
                                                   p.nI, p.istates, X, X + h, B);
