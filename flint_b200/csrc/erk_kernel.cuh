@@ -1143,10 +1143,11 @@ __global__ void __launch_bounds__(128) erk_event_kernel(const __grid_constant__ 
  *   p.dense_eval != 0: FUSED Interpolate -- the coefficients go to shared memory and the CTA evaluates the grid points that lie
  *       in its 128 steps (interp_eval.cuh) straight into Yarr: Bip never exists in HBM (config 4: 58 GB less written and read
  *       per 2^18 orbits, and a store of 2n+2 instead of (pstar+1)*nI doubles per step).
- * resident CTAs per SM: 3 (168 registers) where the stage set fits them, else 2 -- measured per 2^16 planar CR3BP orbits:
- * DOP853 26.9 ms (2) / 25.5 (3) / 28.1 (4); Verner98R 27.9 / 30.7 / 38.9 (spills) */
+ * resident CTAs per SM: 3 (168 registers) where the stage set and the prefetched log fit them (DOP54, Verner65E), else 2 --
+ * measured per 2^16 planar CR3BP orbits, kernel alone (ncu): Verner65E 22.9 ms (3) / 25.8 (2); DOP853 14.0 (3, 184 bytes of
+ * spills since the log prefetch) / 9.7 (2); Verner98R spills at 3 */
 #ifndef FLINT_DENSE_MIN_BLOCKS
-#define FLINT_DENSE_MIN_BLOCKS(METHOD) ((METHOD::NSLOT) <= 12 ? 3 : 2)
+#define FLINT_DENSE_MIN_BLOCKS(METHOD) ((METHOD::NSLOT) <= 8 ? 3 : 2)
 #endif
 template <class METHOD> __host__ __device__ constexpr int dense_smem_doubles(int nI) { return dense_smem_doubles_ps(METHOD::PSTAR, nI); }
 template <class METHOD, class SYS, bool FMA>

@@ -6,8 +6,9 @@ import flint_b200 as F
 from flint_b200 import problems as P
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+method = {"v98r": F.ERK_VERNER98R, "dop853": F.ERK_DOP853, "dop54": F.ERK_DOP54, "v65e": F.ERK_VERNER65E}[sys.argv[3] if len(sys.argv) > 3 else "v98r"]
 G = 10000
-sys_, erk, ikw, xf = P.cr3bp_config3(method=F.ERK_VERNER98R, rtol=1e-11, arith=0, interp_on=True)
+sys_, erk, ikw, xf = P.cr3bp_config3(method=method, rtol=1e-11, arith=0, interp_on=True)
 y0 = torch.from_numpy(P.cr3bp_ensemble(N)).cuda()
 for _ in range(2):
     r = erk.IntegrateBatch(0.0, y0, xf, StepSz=0.0, dense_cap=640, dense_mode=mode, **ikw)
